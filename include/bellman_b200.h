@@ -1,0 +1,176 @@
+/*
+ * bellman_b200.h -- C ABI of the B200-native trust-region subproblem solver.
+ *
+ * Drop-in boundary for the reference's two hot-path functions (paths relative to the
+ * reference repository Jonas477/mixed-integer-optimal-control---algorithm-tools):
+ *
+ *     bellman_TRM!(∇f, u_old, B, β, p, Δt, nu, U, Φ, iterator)     HelpFunctions.jl:20-83
+ *     eval_u_TRM!(u, u_old, U, Φ, B, nu)                            HelpFunctions.jl:98-124
+ *
+ * both called only from TRM (multi-trust.jl:108-114).  The reference has no FFI of its own; a
+ * Julia file loaded after `include("multi-trust.jl")` re-defines the two methods and forwards to
+ * this library through `ccall` (see INTEGRATION.md and julia/BellmanB200.jl).
+ *
+ * Conventions
+ *   - every entry point returns int: 0 = BB200_OK, otherwise an error code; the message of the
+ *     last failure on the calling thread is available from bb200_last_error().  Nothing throws,
+ *     aborts or exits across this boundary.
+ *   - all pointers are HOST pointers unless the parameter name starts with `d_`.
+ *   - host arrays use the reference's (Julia, column-major) memory layout:
+ *         df, u_old, u : double[n][M]      element (m,i) at (i-1)*M + (m-1)        (Julia M x n)
+ *         Phi          : double[2][G][B+1]  Julia Float64[B+1, L1..LM, 2]           (multi-trust.jl:77)
+ *         U            : int64 [n-1][G][B+1][M]  Julia Int64[M, B+1, L1..LM, n-1]   (multi-trust.jl:71-76)
+ *     with G = prod(grid_dims) and grid cells addressed by their column-major offset.
+ *   - the caller owns all host memory; the plan owns all device memory.
+ *   - every entry point selects the plan's device itself and holds a per-plan mutex, so a plan may
+ *     be driven from any OS thread (Julia tasks migrate); distinct plans may run concurrently.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef BELLMAN_B200_H
+#define BELLMAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB200_OK 0
+#define BB200_ERR_ARG 1      /* invalid argument / shape                                           */
+#define BB200_ERR_CUDA 2     /* CUDA runtime failure (message has the CUDA error string)           */
+#define BB200_ERR_INEXACT 3  /* u_old not integer valued / not finite: Julia's InexactError,       */
+                             /* HelpFunctions.jl:37,57 (convert(Int64, abs(numl - u_old[m,i])))    */
+#define BB200_ERR_STALE 4    /* selection/backtrack reached a cell the DP never wrote (the          */
+                             /* reference would read stale U there)                     */
+#define BB200_ERR_STATE 5    /* call order violated (e.g. backtrack before any DP)                 */
+#define BB200_ERR_NOMEM 6    /* device or host allocation failed                                   */
+
+/* plan flags */
+#define BB200_FLAG_STAGE_KERNELS 1u /* force the one-launch-per-stage kernels (validation path)    */
+#define BB200_FLAG_NO_GRAPH 2u      /* do not capture TR iterations into a CUDA graph              */
+#define BB200_FLAG_KEEP_ALL_PHI 4u  /* debug: keep every stage's value rows (tests only, small n)  */
+
+typedef struct bb200_plan bb200_plan;
+
+const char *bb200_last_error(void);
+/* Library/ABI version (major*1000+minor). */
+int bb200_version(void);
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int bb200_device_count(void);
+
+/*
+ * One plan per TRM run (replaces the table allocation at multi-trust.jl:69-77).
+ *   n, M            size(u_old) = (M, n)                                  HelpFunctions.jl:23
+ *   K               number of admissible level tuples, in iterator order  AdmissibleIterators.jl:9-34
+ *   B               budget floor(Δ⁰/Δt)                                   multi-trust.jl:69
+ *   grid_dims[M]    L_m = length(nu[m])
+ *   level_values    int32[K][M], nu[m][l_k[m]]
+ *   grid_offset     int64[K], 0-based column-major offset of tuple k in the L1 x .. x LM grid
+ *   jump_cost       double[K][K], jump_cost[j*K + l] = β * (Σ_m |ν_j[m]-ν_l[m]|^p)^(1/p), evaluated by
+ *                   the CALLER with the reference's own expression (HelpFunctions.jl:63-67); j is the
+ *                   level at stage i+1, l the level at stage i
+ *   dt              Δt
+ *   batch           number of resident subproblem slots (>= 1); each slot has its own df, u_old, u,
+ *                   value rows and argmin table
+ */
+int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B,
+                      const int64_t *grid_dims, const int32_t *level_values,
+                      const int64_t *grid_offset, const double *jump_cost, double dt,
+                      int32_t batch, uint32_t flags, bb200_plan **out);
+int bb200_plan_destroy(bb200_plan *plan);
+
+/* Run subsequent work of this plan on the given cudaStream_t (e.g. torch's current stream)
+ * instead of the plan's own stream.  NULL restores the plan's stream. */
+int bb200_plan_set_stream(bb200_plan *plan, void *cuda_stream);
+
+/*
+ * bellman_TRM!  (HelpFunctions.jl:20-83) for slot 0: copies df and u_old in, runs the DP for budget
+ * B and returns when the value rows and the packed argmin table are resident and consumable.
+ */
+int bb200_bellman(bb200_plan *plan, const double *df, const double *u_old);
+
+/*
+ * eval_u_TRM!  (HelpFunctions.jl:98-124) for slot 0 against the resident table; B_new <= B; may be
+ * called repeatedly with shrinking B_new without re-running the DP (multi-trust.jl:105-114).
+ *   u_out           double[n][M]
+ *   phi_star        value of the selected stage-1 cell           (may be NULL)
+ *   b_star          its budget row                               (may be NULL)
+ *   k_star          its admissible index, 0-based                (may be NULL)
+ */
+int bb200_select_and_backtrack(bb200_plan *plan, int64_t B_new, double *u_out, double *phi_star,
+                               int64_t *b_star, int64_t *k_star);
+
+/* One whole TR inner iteration for slot 0: H2D(df,u_old) -> DP -> selection -> backtrack -> D2H(u),
+ * replayed from a captured CUDA graph unless BB200_FLAG_NO_GRAPH.  Same results as bb200_bellman
+ * followed by bb200_select_and_backtrack(B_new). */
+int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t B_new,
+                double *u_out, double *phi_star, int64_t *b_star, int64_t *k_star);
+
+/* Batched variants: S independent subproblems (own df, u_old) sharing the plan's tables, processed in
+ * waves of `batch` slots.  df_all/u_old_all: double[S][n][M].  For every subproblem, n_radii
+ * selections/backtracks are taken from its one table (a radius sweep costs one DP, multi-trust.jl:109-110):
+ *   u_out_all       double[S][n_radii][n][M]   (may be NULL: only the optima are returned)
+ *   phi_star/b_star/k_star   [S][n_radii]       (each may be NULL)
+ */
+int bb200_solve_batched(bb200_plan *plan, int64_t S, const double *df_all, const double *u_old_all,
+                        int32_t n_radii, const int64_t *B_new, double *u_out_all, double *phi_star,
+                        int64_t *b_star, int64_t *k_star);
+
+/* Deterministic best-candidate reduction over gathered (value, global index) records: smallest
+ * value wins, ties go to the smallest index; NaN never wins against a number.  Used after the
+ * per-rank records were exchanged (ncclAllGather / torch.distributed.all_gather). */
+int bb200_best_candidate(const double *values, const int64_t *indices, int64_t count,
+                         double *best_value, int64_t *best_index);
+
+/* ---- resident (device-side) interface: what bench.py times with inputs already in HBM -------- */
+/* H2D copy of one subproblem's inputs into slot `slot` (asynchronous on the plan's stream). */
+int bb200_upload(bb200_plan *plan, int32_t slot, const double *df, const double *u_old);
+/* Same, from DEVICE pointers (e.g. torch tensors): device-to-device on the plan's stream. */
+int bb200_upload_device(bb200_plan *plan, int32_t slot, const double *d_df, const double *d_u_old);
+/* Launch the DP for slots [slot0, slot0+count) on resident inputs; asynchronous. */
+int bb200_bellman_resident(bb200_plan *plan, int32_t slot0, int32_t count);
+/* Selection + backtrack for one slot on the device; u stays resident; asynchronous. */
+int bb200_backtrack_resident(bb200_plan *plan, int32_t slot, int64_t B_new);
+/* D2H of slot's u and optimum record; synchronises the plan's stream. */
+int bb200_download(bb200_plan *plan, int32_t slot, double *u_out, double *phi_star, int64_t *b_star,
+                   int64_t *k_star);
+/* Block until everything queued on the plan's stream is done; reports deferred device-side errors
+ * (BB200_ERR_INEXACT / BB200_ERR_STALE). */
+int bb200_sync(bb200_plan *plan);
+
+/* ---- parity / inspection --------------------------------------------------------------------- */
+/* Reference-shaped value table (S7): Phi_out double[2][G][B+1]; +Inf in inadmissible grid cells. */
+int bb200_export_phi(bb200_plan *plan, int32_t slot, double *Phi_out);
+/* Reference-shaped argmin table for stages [i0, i1) (1-based, i1 <= n): U_out int64[i1-i0][G][B+1][M]
+ * holding 1-based index tuples; `fill` in cells the DP did not write (the reference leaves those
+ * stale). */
+int bb200_export_argmin(bb200_plan *plan, int32_t slot, int64_t i0, int64_t i1, int64_t *U_out,
+                        int64_t fill);
+/* Exact number of executions of the innermost loop body (HelpFunctions.jl:71-76) of the last DP of
+ * `slot`: N = Σ_i K·Σ_l max(0, B+1-b~_l(i)). */
+int bb200_count_updates(bb200_plan *plan, int32_t slot, int64_t *n_updates);
+
+/* Device-side "next" rows: evaluated on the resident u / u_old / df of `slot`.
+ *   pred integral Δt·Σ_j ∇f[:,j]'(u_old[:,j]-u[:,j])  (multi-trust.jl:117-121)
+ *   TV_p(u, p)  with p = +Inf, 1 or 2                    (HelpFunctions.jl:251-268)          */
+int bb200_pred_integral(bb200_plan *plan, int32_t slot, double *int_val);
+int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
+
+/* Statistics of the plan.  Index meaning (values beyond `count` are not written):
+ *   0 last DP device time [ms] (CUDA events on the launching stream, all slots of the launch)
+ *   1 last selection+backtrack device time [ms]
+ *   2 kernels launched by this plan so far
+ *   3 kernel path of the last DP: 0 = per-stage kernels, 1 = persistent wavefront kernel
+ *   4 CTAs used by the last DP launch          5 source rows per CTA
+ *   6 argmin bytes per cell (1 or 2)           7 device bytes owned by the plan
+ *   8 threads per CTA of the last DP launch    9 j-split of the last DP launch
+ */
+int bb200_stats(bb200_plan *plan, double *out, int32_t count);
+
+/* Tuning knobs for experiments (0 = automatic): number of CTAs, j-split, rows per thread. */
+int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BELLMAN_B200_H */

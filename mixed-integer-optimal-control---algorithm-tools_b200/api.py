@@ -1,0 +1,219 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+    bellman_TRM(df, u_old, B, beta, p, dt, nu, U, Phi, iterator)    HelpFunctions.jl:20
+    eval_u_TRM(u, u_old, U, Phi, B, nu)                             HelpFunctions.jl:98
+
+Same names, argument order and meaning as the reference; arrays use the reference's memory layout, which
+in C-order numpy reads  df/u_old/u: (n, M),  Phi: (2, LM, .., L1, B+1),  U: (n-1, LM, .., L1, B+1, M).
+Everything is forwarded to the C ABI (include/bellman_b200.h); nothing is computed in Python.
+
+`TRMPlan` is the object the Julia glue keeps per `TRM` run (keyed on objectid(U)); the two free functions
+keep one plan per `U` array the same way, so a transliterated TRM loop runs unchanged.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+
+import numpy as np
+
+from . import _lib
+from .iterators import flatten, jump_cost_table
+
+
+def _as_io(a, n, M, name):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != (n, M):
+        raise ValueError(f"{name} must have shape (n, M) = ({n}, {M}); got {a.shape}")
+    return a
+
+
+class TRMPlan:
+    """Device-resident state of one TRM run: tables, value rows, packed argmin table (multi-trust.jl:69-77)."""
+
+    def __init__(self, nu, iterator, n, B, beta, p, dt, *, device=0, batch=1, flags=0, cost=None):
+        self.lib = _lib.load()
+        self.nu = [list(map(int, v)) for v in nu]
+        self.level_values, self.grid_offset, self.grid_dims = flatten(self.nu, iterator)
+        self.n, self.M, self.K, self.B = int(n), len(self.nu), int(self.level_values.shape[0]), int(B)
+        self.dt = float(dt)
+        self.batch = int(batch)
+        if cost is None:
+            cost = jump_cost_table(beta, p, self.level_values)
+        self.cost = np.ascontiguousarray(cost, dtype=np.float64)
+        if self.cost.shape != (self.K, self.K):
+            raise ValueError("jump cost table must be K x K")
+        handle = _lib.c_plan_p()
+        _lib.check(self.lib.bb200_plan_create(
+            int(device), self.n, self.M, self.K, self.B, _lib.i64p(self.grid_dims),
+            _lib.i32p(np.ascontiguousarray(self.level_values)), _lib.i64p(self.grid_offset),
+            _lib.f64p(self.cost), self.dt, self.batch, int(flags), ctypes.byref(handle)))
+        self._h = handle
+        self._fin = weakref.finalize(self, self.lib.bb200_plan_destroy, handle)
+
+    # ---- reference-shaped entry points ---------------------------------------------------------
+    def bellman(self, df, u_old):
+        """bellman_TRM! for budget B (HelpFunctions.jl:20-83)."""
+        df = _as_io(df, self.n, self.M, "df")
+        u_old = _as_io(u_old, self.n, self.M, "u_old")
+        _lib.check(self.lib.bb200_bellman(self._h, _lib.f64p(df), _lib.f64p(u_old)))
+
+    def eval_u(self, u, B_new=None):
+        """eval_u_TRM! (HelpFunctions.jl:98-124); returns (phi_star, b_star, k_star)."""
+        if u.dtype != np.float64 or not u.flags.c_contiguous or u.shape != (self.n, self.M):
+            raise ValueError("u must be a C-contiguous float64 (n, M) array")
+        ps, bs, ks = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.bb200_select_and_backtrack(
+            self._h, self.B if B_new is None else int(B_new), _lib.f64p(u), ctypes.byref(ps),
+            ctypes.byref(bs), ctypes.byref(ks)))
+        return ps.value, bs.value, ks.value
+
+    def solve(self, df, u_old, u, B_new=None):
+        """One TR inner iteration: DP + selection + backtrack in one call."""
+        df = _as_io(df, self.n, self.M, "df")
+        u_old = _as_io(u_old, self.n, self.M, "u_old")
+        ps, bs, ks = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.bb200_solve(
+            self._h, _lib.f64p(df), _lib.f64p(u_old), self.B if B_new is None else int(B_new),
+            _lib.f64p(u), ctypes.byref(ps), ctypes.byref(bs), ctypes.byref(ks)))
+        return ps.value, bs.value, ks.value
+
+    def solve_batched(self, df_all, u_old_all, radii, want_u=True):
+        """S independent subproblems, each with len(radii) selections from its one table."""
+        df_all = np.ascontiguousarray(df_all, dtype=np.float64)
+        u_old_all = np.ascontiguousarray(u_old_all, dtype=np.float64)
+        S = df_all.shape[0]
+        if df_all.shape != (S, self.n, self.M) or u_old_all.shape != df_all.shape:
+            raise ValueError("df_all/u_old_all must have shape (S, n, M)")
+        radii = np.ascontiguousarray(radii, dtype=np.int64)
+        R = radii.shape[0]
+        u_out = np.empty((S, R, self.n, self.M), dtype=np.float64) if want_u else None
+        phi = np.empty((S, R), dtype=np.float64)
+        bs = np.empty((S, R), dtype=np.int64)
+        ks = np.empty((S, R), dtype=np.int64)
+        _lib.check(self.lib.bb200_solve_batched(
+            self._h, S, _lib.f64p(df_all), _lib.f64p(u_old_all), R, _lib.i64p(radii),
+            _lib.f64p(u_out), _lib.f64p(phi), _lib.i64p(bs), _lib.i64p(ks)))
+        return u_out, phi, bs, ks
+
+    # ---- resident interface --------------------------------------------------------------------
+    def upload(self, slot, df, u_old):
+        df = _as_io(df, self.n, self.M, "df")
+        u_old = _as_io(u_old, self.n, self.M, "u_old")
+        _lib.check(self.lib.bb200_upload(self._h, slot, _lib.f64p(df), _lib.f64p(u_old)))
+        _lib.check(self.lib.bb200_sync(self._h))  # the numpy temporaries may die after return
+
+    def upload_device(self, slot, d_df_ptr, d_u_old_ptr):
+        _lib.check(self.lib.bb200_upload_device(self._h, slot, ctypes.c_void_p(d_df_ptr),
+                                                ctypes.c_void_p(d_u_old_ptr)))
+
+    def bellman_resident(self, slot0=0, count=1):
+        _lib.check(self.lib.bb200_bellman_resident(self._h, slot0, count))
+
+    def backtrack_resident(self, slot=0, B_new=None):
+        _lib.check(self.lib.bb200_backtrack_resident(self._h, slot, self.B if B_new is None else int(B_new)))
+
+    def download(self, slot, u):
+        ps, bs, ks = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.bb200_download(self._h, slot, _lib.f64p(u), ctypes.byref(ps), ctypes.byref(bs),
+                                           ctypes.byref(ks)))
+        return ps.value, bs.value, ks.value
+
+    def sync(self):
+        _lib.check(self.lib.bb200_sync(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        _lib.check(self.lib.bb200_plan_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def tune(self, ctas=0, jsplit=0, variant=0):
+        _lib.check(self.lib.bb200_plan_tune(self._h, ctas, jsplit, variant))
+
+    # ---- inspection ----------------------------------------------------------------------------
+    def export_phi(self, slot=0):
+        """Reference-shaped value table (2, LM, .., L1, B+1); +Inf in inadmissible grid cells."""
+        out = np.empty((2, *reversed([int(d) for d in self.grid_dims]), self.B + 1), dtype=np.float64)
+        _lib.check(self.lib.bb200_export_phi(self._h, slot, _lib.f64p(out)))
+        return out
+
+    def export_argmin(self, i0=1, i1=None, fill=0, slot=0):
+        """Reference-shaped argmin table for stages [i0, i1): (i1-i0, LM, .., L1, B+1, M)."""
+        i1 = self.n if i1 is None else i1
+        out = np.empty((i1 - i0, *reversed([int(d) for d in self.grid_dims]), self.B + 1, self.M), dtype=np.int64)
+        _lib.check(self.lib.bb200_export_argmin(self._h, slot, i0, i1, _lib.i64p(out), fill))
+        return out
+
+    def count_updates(self, slot=0):
+        v = ctypes.c_int64()
+        _lib.check(self.lib.bb200_count_updates(self._h, slot, ctypes.byref(v)))
+        return v.value
+
+    def pred_integral(self, slot=0):
+        v = ctypes.c_double()
+        _lib.check(self.lib.bb200_pred_integral(self._h, slot, ctypes.byref(v)))
+        return v.value
+
+    def tv(self, p, slot=0):
+        v = ctypes.c_double()
+        _lib.check(self.lib.bb200_tv(self._h, slot, float(p), ctypes.byref(v)))
+        return v.value
+
+    def stats(self):
+        out = np.zeros(10, dtype=np.float64)
+        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 10))
+        keys = ("dp_ms", "backtrack_ms", "launches", "path", "ctas", "rows_per_cta", "arg_bytes",
+                "device_bytes", "threads", "jsplit")
+        return dict(zip(keys, out.tolist()))
+
+    def close(self):
+        self._fin()
+
+
+# ---- drop-in free functions (one plan per U array, like the Julia glue's objectid(U) key) -----------
+_plans: dict = {}
+
+
+def _plan_for(U, Phi, builder):
+    key = id(U) if U is not None else id(Phi)
+    ent = _plans.get(key)
+    if ent is None:
+        if builder is None:
+            raise _lib.BellmanB200Error(_lib.ERR_STATE, "eval_u_TRM called before bellman_TRM for these tables")
+        ent = builder()
+        _plans[key] = ent
+        anchor = U if U is not None else Phi
+        try:
+            weakref.finalize(anchor, _plans.pop, key, None)
+        except TypeError:
+            pass
+    return ent
+
+
+def bellman_TRM(df, u_old, B, beta, p, dt, nu, U, Phi, iterator, *, device=0, write_back=False):
+    """Drop-in for bellman_TRM! (HelpFunctions.jl:20).  The device keeps its own packed tables; the
+    caller's U/Phi are only filled when write_back=True (parity/debug)."""
+    u_old_a = np.asarray(u_old)
+    n, M = u_old_a.shape
+    it = list(iterator)
+
+    def build():
+        return TRMPlan(nu, it, n, B, beta, p, dt, device=device)
+
+    plan = _plan_for(U, Phi, build)
+    if (plan.n, plan.M, plan.B) != (n, M, int(B)):
+        raise ValueError("tables were created for a different problem size")
+    plan.bellman(df, u_old)
+    if write_back:
+        if Phi is not None:
+            Phi[...] = plan.export_phi()
+        if U is not None and n > 1:
+            U[...] = plan.export_argmin(1, n, fill=0)
+    return None
+
+
+def eval_u_TRM(u, u_old, U, Phi, B, nu, *, info=None):
+    """Drop-in for eval_u_TRM! (HelpFunctions.jl:98); B may be any budget <= the table's."""
+    plan = _plan_for(U, Phi, None)
+    ps, bs, ks = plan.eval_u(u, B)
+    if info is not None:
+        info.update(phi_star=ps, b_star=bs, k_star=ks, g_star=int(plan.grid_offset[ks]) if ks >= 0 else -1)
+    return None

@@ -1,0 +1,660 @@
+// bb200_api.cu -- the C ABI (include/bellman_b200.h): plans, resident buffers, launch sequencing.
+//
+// Replaces, behind plain C entry points, the reference's
+//   table allocation        multi-trust.jl:69-77        -> bb200_plan_create
+//   bellman_TRM!            HelpFunctions.jl:20-83      -> bb200_bellman / bb200_bellman_resident
+//   eval_u_TRM!             HelpFunctions.jl:98-124     -> bb200_select_and_backtrack
+// There is no CPU implementation in this library: every compute entry point needs a CUDA device.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bellman_b200.h"
+#include "bb200_internal.cuh"
+#include "kernels.cuh"
+
+using namespace bb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? BB200_ERR_NOMEM : BB200_ERR_CUDA,    \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct SlotHost {
+    double *df = nullptr, *u_old = nullptr, *u = nullptr, *phi = nullptr, *rec = nullptr;
+    void *arg = nullptr;
+    unsigned long long *n_updates = nullptr;
+    bool has_dp = false;
+};
+
+constexpr int kMaxRadii = 16;
+
+}  // namespace
+
+struct bb200_plan {
+    int device = 0;
+    int64_t n = 0, B = 0, G = 1;
+    int M = 0, K = 0, Kp = 0, B1 = 0, batch = 1, argw = 1;
+    int64_t nPad = 0;
+    double dt = 0.;
+    uint32_t flags = 0;
+    std::vector<int64_t> grid_dims, grid_offset;
+    std::vector<int32_t> level_values;
+    Tables tab{};
+    // device
+    double *d_lvd = nullptr, *d_cost = nullptr, *d_halo = nullptr, *d_scalar = nullptr;
+    long long *d_goff = nullptr;
+    unsigned long long *d_flags = nullptr;
+    int *d_err = nullptr, *d_btmax = nullptr;
+    SlotDev *d_slots = nullptr;
+    std::vector<SlotHost> slots;
+    std::vector<SlotDev> slots_dev;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // pinned staging
+    double *h_rec = nullptr;
+    int *h_err = nullptr;
+    // geometry
+    int num_sms = 0;
+    size_t smem_max = 0;
+    bool wave_ok = false;
+    WaveCfg cfg{};
+    int tune_ctas = 0, tune_js = 0, tune_variant = 0;
+    // stats
+    double last_dp_ms = 0., last_bt_ms = 0.;
+    double launches = 0.;
+    int last_path = -1;
+    size_t dev_bytes = 0;
+    bool dp_timed = false, bt_timed = false;
+    std::mutex mu;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(bb200_plan *p, T **ptr, size_t count)
+{
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    cudaError_t e = cudaMalloc((void **)ptr, bytes);
+    if (e != cudaSuccess)
+        return fail(BB200_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    p->dev_bytes += bytes;
+    return BB200_OK;
+}
+
+int reconfigure(bb200_plan *p)
+{
+    p->wave_ok = false;
+    if (p->flags & BB200_FLAG_STAGE_KERNELS) return BB200_OK;
+    WaveCfg c{};
+    if (wave_configure(p->tab, p->argw, p->num_sms, p->smem_max, p->tune_ctas, p->tune_js, p->tune_variant, c)) {
+        p->cfg = c;
+        p->wave_ok = true;
+    }
+    return BB200_OK;
+}
+
+void destroy_plan(bb200_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->own_stream) cudaStreamSynchronize(p->own_stream);
+    for (auto &s : p->slots) {
+        cudaFree(s.df); cudaFree(s.u_old); cudaFree(s.u); cudaFree(s.phi); cudaFree(s.rec);
+        cudaFree(s.arg); cudaFree(s.n_updates);
+    }
+    cudaFree(p->d_lvd); cudaFree(p->d_cost); cudaFree(p->d_halo); cudaFree(p->d_scalar);
+    cudaFree(p->d_goff); cudaFree(p->d_flags); cudaFree(p->d_err); cudaFree(p->d_btmax);
+    cudaFree(p->d_slots);
+    if (p->h_rec) cudaFreeHost(p->h_rec);
+    if (p->h_err) cudaFreeHost(p->h_err);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+}
+
+// Queue the DP for slots [slot0, slot0+count) on the plan's stream.
+int queue_dp(bb200_plan *p, int slot0, int count)
+{
+    cudaStream_t st = p->stream;
+    CU(cudaEventRecord(p->ev[0], st));
+    CU(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(int), st));
+    CU(cudaMemsetAsync(p->d_btmax, 0, sizeof(int), st));
+    for (int s = slot0; s < slot0 + count; ++s) {
+        CU(cudaMemsetAsync(p->slots[s].n_updates, 0, sizeof(unsigned long long), st));
+        launch_prep(p->tab, p->slots_dev[s], p->d_err, p->d_btmax, st);
+        p->launches += 1;
+        p->slots[s].has_dp = true;
+    }
+    if (p->wave_ok) {
+        CU(cudaMemsetAsync(p->d_flags, 0, (size_t)p->cfg.G * kFlagStride * sizeof(unsigned long long), st));
+        WaveCfg c = p->cfg;
+        c.nsub = count;
+        c.slots = p->d_slots + slot0;
+        c.halo = p->d_halo;
+        c.flags = p->d_flags;
+        c.err = p->d_err;
+        c.btmax = p->d_btmax;
+        CU(launch_wavefront(p->tab, c, p->argw, st));
+        p->launches += 1;
+        p->last_path = 1;
+    } else {
+        for (int s = slot0; s < slot0 + count; ++s) {
+            int l = launch_stage_path(p->tab, p->slots_dev[s], p->argw, st);
+            if (l < 0) return fail(BB200_ERR_ARG, "shape not supported by the per-stage kernels (K=%d)", p->K);
+            p->launches += l;
+        }
+        p->last_path = 0;
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev[1], st));
+    p->dp_timed = true;
+    return BB200_OK;
+}
+
+int queue_backtrack(bb200_plan *p, int slot, int64_t B_new, int rec_idx)
+{
+    if (!p->slots[slot].has_dp) return fail(BB200_ERR_STATE, "slot %d has no DP result yet", slot);
+    if (B_new < 0 || B_new > p->B) return fail(BB200_ERR_ARG, "B_new=%lld outside [0, %lld]", (long long)B_new, (long long)p->B);
+    cudaStream_t st = p->stream;
+    SlotDev sd = p->slots_dev[slot];
+    sd.rec = p->slots[slot].rec + 4 * rec_idx;
+    CU(cudaEventRecord(p->ev[2], st));
+    launch_select(p->tab, sd, (int)B_new, p->d_err, st);
+    launch_backtrack(p->tab, sd, p->argw, p->d_err, st);
+    p->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev[3], st));
+    p->bt_timed = true;
+    return BB200_OK;
+}
+
+// Synchronise and translate the deferred device-side error word.
+int sync_and_check(bb200_plan *p)
+{
+    CU(cudaMemcpyAsync(p->h_err, p->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    if (p->dp_timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->last_dp_ms = ms;
+        p->dp_timed = false;
+    }
+    if (p->bt_timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]) == cudaSuccess) p->last_bt_ms = ms;
+        p->bt_timed = false;
+    }
+    if (p->h_err[2]) return fail(BB200_ERR_CUDA, "wavefront kernel watchdog fired: a pipeline dependency was never satisfied");
+    if (p->h_err[0]) return fail(BB200_ERR_INEXACT, "InexactError: u_old is not integer valued / finite (HelpFunctions.jl:37,57)");
+    if (p->h_err[1]) return fail(BB200_ERR_STALE, "selection/backtrack reached a cell the DP never wrote (no feasible trajectory for this u_old / budget)");
+    return BB200_OK;
+}
+
+int check_slot(bb200_plan *p, int slot)
+{
+    if (!p) return fail(BB200_ERR_ARG, "plan is NULL");
+    if (slot < 0 || slot >= p->batch) return fail(BB200_ERR_ARG, "slot %d outside [0, %d)", slot, p->batch);
+    return BB200_OK;
+}
+
+struct Guard {
+    std::lock_guard<std::mutex> lk;
+    explicit Guard(bb200_plan *p) : lk(p->mu) { cudaSetDevice(p->device); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char *bb200_last_error(void) { return g_err.c_str(); }
+int bb200_version(void) { return 1000; }
+
+int bb200_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, const int64_t *grid_dims,
+                      const int32_t *level_values, const int64_t *grid_offset, const double *jump_cost,
+                      double dt, int32_t batch, uint32_t flags, bb200_plan **out)
+{
+    if (!out) return fail(BB200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!grid_dims || !level_values || !grid_offset || !jump_cost) return fail(BB200_ERR_ARG, "NULL table pointer");
+    if (n < 1 || n > 0x7fffff00ll) return fail(BB200_ERR_ARG, "n=%lld out of range", (long long)n);
+    if (M < 1 || M > kMaxM) return fail(BB200_ERR_ARG, "M=%d out of range [1, %d]", M, kMaxM);
+    if (K < 1 || K > 65534) return fail(BB200_ERR_ARG, "K=%d out of range [1, 65534]", K);
+    if (B < 0 || B > 0x3fffffffll) return fail(BB200_ERR_ARG, "B=%lld out of range", (long long)B);
+    if (batch < 1) return fail(BB200_ERR_ARG, "batch=%d must be >= 1", batch);
+    int64_t G = 1;
+    for (int m = 0; m < M; ++m) {
+        if (grid_dims[m] < 1) return fail(BB200_ERR_ARG, "grid_dims[%d]=%lld", m, (long long)grid_dims[m]);
+        G *= grid_dims[m];
+    }
+    for (int k = 0; k < K; ++k)
+        if (grid_offset[k] < 0 || grid_offset[k] >= G) return fail(BB200_ERR_ARG, "grid_offset[%d] outside the grid", k);
+    int ndev = bb200_device_count();
+    if (ndev == 0) return fail(BB200_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(BB200_ERR_ARG, "device %d outside [0, %d)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    bb200_plan *p = new bb200_plan();
+    p->device = device; p->n = n; p->M = M; p->K = K; p->B = B; p->B1 = (int)(B + 1);
+    p->Kp = (K + 15) / 16 * 16; p->dt = dt; p->batch = batch; p->flags = flags; p->G = G;
+    p->argw = (K <= 255) ? 1 : 2;
+    p->nPad = (n + kChunk - 1) / kChunk * kChunk;
+    p->grid_dims.assign(grid_dims, grid_dims + M);
+    p->grid_offset.assign(grid_offset, grid_offset + K);
+    p->level_values.assign(level_values, level_values + (size_t)K * M);
+    int rc = BB200_OK;
+    auto bail = [&](int code) { destroy_plan(p); return code; };
+
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(BB200_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    p->num_sms = prop.multiProcessorCount;
+    p->smem_max = prop.sharedMemPerBlockOptin;
+
+    // constant tables
+    std::vector<double> lvd((size_t)K * M), cost((size_t)K * p->Kp, std::numeric_limits<double>::infinity());
+    for (size_t x = 0; x < lvd.size(); ++x) lvd[x] = (double)level_values[x];
+    for (int j = 0; j < K; ++j)
+        for (int l = 0; l < K; ++l) cost[(size_t)j * p->Kp + l] = jump_cost[(size_t)j * K + l];
+    std::vector<long long> goff(grid_offset, grid_offset + K);
+    if ((rc = dev_alloc(p, &p->d_lvd, lvd.size()))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_cost, cost.size()))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_goff, goff.size()))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_err, 4))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_btmax, 1))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_scalar, 8))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_flags, (size_t)prop.multiProcessorCount * kFlagStride))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_halo, (size_t)kHaloRing * p->B1 * p->Kp))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_slots, (size_t)batch))) return bail(rc);
+#define CUB(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return bail(fail(BB200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));      \
+    } while (0)
+    CUB(cudaMemcpy(p->d_lvd, lvd.data(), lvd.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(p->d_cost, cost.data(), cost.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUB(cudaMemcpy(p->d_goff, goff.data(), goff.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CUB(cudaMemset(p->d_err, 0, 4 * sizeof(int)));
+
+    p->tab.n = (int)n; p->tab.M = M; p->tab.K = K; p->tab.Kp = p->Kp; p->tab.B1 = p->B1; p->tab.dt = dt;
+    p->tab.lvd = p->d_lvd; p->tab.cost = p->d_cost; p->tab.goff = p->d_goff;
+
+    p->slots.resize(batch);
+    p->slots_dev.resize(batch);
+    const size_t io = (size_t)p->nPad * M;
+    const size_t argcells = (size_t)(n > 1 ? n - 1 : 1) * p->B1 * p->Kp;
+    for (int s = 0; s < batch; ++s) {
+        SlotHost &h = p->slots[s];
+        if ((rc = dev_alloc(p, &h.df, io))) return bail(rc);
+        if ((rc = dev_alloc(p, &h.u_old, io))) return bail(rc);
+        if ((rc = dev_alloc(p, &h.u, io))) return bail(rc);
+        if ((rc = dev_alloc(p, &h.phi, (size_t)2 * p->B1 * p->Kp))) return bail(rc);
+        if ((rc = dev_alloc(p, &h.rec, (size_t)4 * kMaxRadii))) return bail(rc);
+        if ((rc = dev_alloc(p, &h.n_updates, 1))) return bail(rc);
+        unsigned char *a = nullptr;
+        if ((rc = dev_alloc(p, &a, argcells * p->argw))) return bail(rc);
+        h.arg = a;
+        CUB(cudaMemset(h.df, 0, io * sizeof(double)));
+        CUB(cudaMemset(h.u_old, 0, io * sizeof(double)));
+        CUB(cudaMemset(h.u, 0, io * sizeof(double)));
+        SlotDev &d = p->slots_dev[s];
+        d.df = h.df; d.u_old = h.u_old; d.u = h.u; d.phi = h.phi; d.arg = h.arg;
+        d.n_updates = h.n_updates; d.rec = h.rec;
+    }
+    CUB(cudaMemcpy(p->d_slots, p->slots_dev.data(), sizeof(SlotDev) * batch, cudaMemcpyHostToDevice));
+    CUB(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    p->stream = p->own_stream;
+    for (auto &e : p->ev) CUB(cudaEventCreate(&e));
+    CUB(cudaMallocHost((void **)&p->h_rec, 4 * kMaxRadii * sizeof(double)));
+    CUB(cudaMallocHost((void **)&p->h_err, 4 * sizeof(int)));
+#undef CUB
+    reconfigure(p);
+    *out = p;
+    return BB200_OK;
+}
+
+int bb200_plan_destroy(bb200_plan *plan)
+{
+    if (!plan) return BB200_OK;
+    destroy_plan(plan);
+    return BB200_OK;
+}
+
+int bb200_plan_set_stream(bb200_plan *plan, void *cuda_stream)
+{
+    if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
+    Guard g(plan);
+    CU(cudaStreamSynchronize(plan->stream));
+    plan->stream = cuda_stream ? (cudaStream_t)cuda_stream : plan->own_stream;
+    return BB200_OK;
+}
+
+int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t variant)
+{
+    if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
+    Guard g(plan);
+    plan->tune_ctas = ctas; plan->tune_js = jsplit; plan->tune_variant = variant;
+    reconfigure(plan);
+    if (!plan->wave_ok && !(plan->flags & BB200_FLAG_STAGE_KERNELS) && (ctas || jsplit || variant))
+        return fail(BB200_ERR_ARG, "requested tuning (ctas=%d, jsplit=%d, variant=%d) is not launchable", ctas, jsplit, variant);
+    return BB200_OK;
+}
+
+int bb200_upload(bb200_plan *plan, int32_t slot, const double *df, const double *u_old)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    if (!df || !u_old) return fail(BB200_ERR_ARG, "df/u_old is NULL");
+    Guard g(plan);
+    const size_t bytes = (size_t)plan->n * plan->M * sizeof(double);
+    CU(cudaMemcpyAsync(plan->slots[slot].df, df, bytes, cudaMemcpyHostToDevice, plan->stream));
+    CU(cudaMemcpyAsync(plan->slots[slot].u_old, u_old, bytes, cudaMemcpyHostToDevice, plan->stream));
+    return BB200_OK;
+}
+
+int bb200_upload_device(bb200_plan *plan, int32_t slot, const double *d_df, const double *d_u_old)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    if (!d_df || !d_u_old) return fail(BB200_ERR_ARG, "d_df/d_u_old is NULL");
+    Guard g(plan);
+    const size_t bytes = (size_t)plan->n * plan->M * sizeof(double);
+    CU(cudaMemcpyAsync(plan->slots[slot].df, d_df, bytes, cudaMemcpyDeviceToDevice, plan->stream));
+    CU(cudaMemcpyAsync(plan->slots[slot].u_old, d_u_old, bytes, cudaMemcpyDeviceToDevice, plan->stream));
+    return BB200_OK;
+}
+
+int bb200_bellman_resident(bb200_plan *plan, int32_t slot0, int32_t count)
+{
+    int rc = check_slot(plan, slot0);
+    if (rc) return rc;
+    if (count < 1 || slot0 + count > plan->batch) return fail(BB200_ERR_ARG, "slot range [%d, %d) outside the plan", slot0, slot0 + count);
+    Guard g(plan);
+    return queue_dp(plan, slot0, count);
+}
+
+int bb200_backtrack_resident(bb200_plan *plan, int32_t slot, int64_t B_new)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    Guard g(plan);
+    return queue_backtrack(plan, slot, B_new, 0);
+}
+
+int bb200_sync(bb200_plan *plan)
+{
+    if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
+    Guard g(plan);
+    return sync_and_check(plan);
+}
+
+static int download_locked(bb200_plan *plan, int slot, int rec_idx, double *u_out, double *phi_star,
+                           int64_t *b_star, int64_t *k_star)
+{
+    if (u_out)
+        CU(cudaMemcpyAsync(u_out, plan->slots[slot].u, (size_t)plan->n * plan->M * sizeof(double),
+                           cudaMemcpyDeviceToHost, plan->stream));
+    CU(cudaMemcpyAsync(plan->h_rec, plan->slots[slot].rec + 4 * rec_idx, 4 * sizeof(double),
+                       cudaMemcpyDeviceToHost, plan->stream));
+    int rc = sync_and_check(plan);
+    if (phi_star) *phi_star = plan->h_rec[0];
+    if (b_star) *b_star = (int64_t)plan->h_rec[1];
+    if (k_star) *k_star = (int64_t)plan->h_rec[2];
+    return rc;
+}
+
+int bb200_download(bb200_plan *plan, int32_t slot, double *u_out, double *phi_star, int64_t *b_star,
+                   int64_t *k_star)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    Guard g(plan);
+    return download_locked(plan, slot, 0, u_out, phi_star, b_star, k_star);
+}
+
+int bb200_bellman(bb200_plan *plan, const double *df, const double *u_old)
+{
+    int rc = bb200_upload(plan, 0, df, u_old);
+    if (rc) return rc;
+    Guard g(plan);
+    rc = queue_dp(plan, 0, 1);
+    if (rc) return rc;
+    return sync_and_check(plan);
+}
+
+int bb200_select_and_backtrack(bb200_plan *plan, int64_t B_new, double *u_out, double *phi_star,
+                               int64_t *b_star, int64_t *k_star)
+{
+    if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
+    if (!u_out) return fail(BB200_ERR_ARG, "u_out is NULL");
+    Guard g(plan);
+    int rc = queue_backtrack(plan, 0, B_new, 0);
+    if (rc) return rc;
+    return download_locked(plan, 0, 0, u_out, phi_star, b_star, k_star);
+}
+
+int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t B_new, double *u_out,
+                double *phi_star, int64_t *b_star, int64_t *k_star)
+{
+    int rc = bb200_upload(plan, 0, df, u_old);
+    if (rc) return rc;
+    if (!u_out) return fail(BB200_ERR_ARG, "u_out is NULL");
+    Guard g(plan);
+    rc = queue_dp(plan, 0, 1);
+    if (rc) return rc;
+    rc = queue_backtrack(plan, 0, B_new, 0);
+    if (rc) return rc;
+    return download_locked(plan, 0, 0, u_out, phi_star, b_star, k_star);
+}
+
+int bb200_solve_batched(bb200_plan *plan, int64_t S, const double *df_all, const double *u_old_all,
+                        int32_t n_radii, const int64_t *B_new, double *u_out_all, double *phi_star,
+                        int64_t *b_star, int64_t *k_star)
+{
+    if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
+    if (S < 1 || !df_all || !u_old_all) return fail(BB200_ERR_ARG, "bad batch arguments");
+    if (n_radii < 1 || n_radii > kMaxRadii || !B_new) return fail(BB200_ERR_ARG, "n_radii=%d outside [1, %d]", n_radii, kMaxRadii);
+    Guard g(plan);
+    const size_t io = (size_t)plan->n * plan->M;
+    int worst = BB200_OK;
+    std::string worst_msg;
+    for (int64_t s0 = 0; s0 < S; s0 += plan->batch) {
+        const int cnt = (int)std::min<int64_t>(plan->batch, S - s0);
+        for (int s = 0; s < cnt; ++s) {
+            CU(cudaMemcpyAsync(plan->slots[s].df, df_all + (size_t)(s0 + s) * io, io * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
+            CU(cudaMemcpyAsync(plan->slots[s].u_old, u_old_all + (size_t)(s0 + s) * io, io * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
+        }
+        int rc = queue_dp(plan, 0, cnt);
+        if (rc) return rc;
+        for (int s = 0; s < cnt; ++s)
+            for (int r = 0; r < n_radii; ++r) {
+                rc = queue_backtrack(plan, s, B_new[r], r);
+                if (rc) return rc;
+                const size_t o = (size_t)(s0 + s) * n_radii + r;
+                rc = download_locked(plan, s, r, u_out_all ? u_out_all + o * io : nullptr,
+                                     phi_star ? phi_star + o : nullptr, b_star ? b_star + o : nullptr,
+                                     k_star ? k_star + o : nullptr);
+                if (rc == BB200_ERR_CUDA) return rc;
+                if (rc && !worst) { worst = rc; worst_msg = g_err; }
+            }
+    }
+    if (worst) g_err = worst_msg;
+    return worst;
+}
+
+int bb200_best_candidate(const double *values, const int64_t *indices, int64_t count, double *best_value,
+                         int64_t *best_index)
+{
+    if (!values || !indices || count < 1 || !best_value || !best_index) return fail(BB200_ERR_ARG, "bad arguments");
+    double bv = values[0];
+    int64_t bi = indices[0];
+    for (int64_t x = 1; x < count; ++x) {
+        const double v = values[x];
+        const bool better = (v < bv) || (bv != bv && v == v) || (v == bv && indices[x] < bi) ||
+                            (v != v && bv != bv && indices[x] < bi);
+        if (better) { bv = v; bi = indices[x]; }
+    }
+    *best_value = bv;
+    *best_index = bi;
+    return BB200_OK;
+}
+
+int bb200_export_phi(bb200_plan *plan, int32_t slot, double *Phi_out)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    if (!Phi_out) return fail(BB200_ERR_ARG, "Phi_out is NULL");
+    Guard g(plan);
+    if (!plan->slots[slot].has_dp) return fail(BB200_ERR_STATE, "slot %d has no DP result yet", slot);
+    const size_t cells = (size_t)2 * plan->B1 * plan->Kp;
+    std::vector<double> h(cells);
+    CU(cudaStreamSynchronize(plan->stream));
+    CU(cudaMemcpy(h.data(), plan->slots[slot].phi, cells * sizeof(double), cudaMemcpyDeviceToHost));
+    const size_t B1 = plan->B1;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (size_t x = 0; x < 2 * (size_t)plan->G * B1; ++x) Phi_out[x] = inf;
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < plan->K; ++k)
+            for (size_t b = 0; b < B1; ++b)
+                Phi_out[b + B1 * ((size_t)plan->grid_offset[k] + (size_t)plan->G * s)] = h[((size_t)s * B1 + b) * plan->Kp + k];
+    // n == 1: the reference never touches slot 2 (it keeps the caller's contents); we report +Inf there.
+    return BB200_OK;
+}
+
+int bb200_export_argmin(bb200_plan *plan, int32_t slot, int64_t i0, int64_t i1, int64_t *U_out, int64_t fill)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    if (!U_out) return fail(BB200_ERR_ARG, "U_out is NULL");
+    if (i0 < 1 || i1 > plan->n || i0 > i1) return fail(BB200_ERR_ARG, "stage range [%lld, %lld) invalid", (long long)i0, (long long)i1);
+    Guard g(plan);
+    if (!plan->slots[slot].has_dp) return fail(BB200_ERR_STATE, "slot %d has no DP result yet", slot);
+    CU(cudaStreamSynchronize(plan->stream));
+    const size_t B1 = plan->B1, Kp = plan->Kp;
+    const int M = plan->M, K = plan->K;
+    const size_t rows = (size_t)(i1 - i0);
+    if (rows == 0) return BB200_OK;
+    std::vector<unsigned char> a(rows * B1 * Kp * plan->argw);
+    std::vector<double> uo(rows * M);
+    CU(cudaMemcpy(a.data(), (unsigned char *)plan->slots[slot].arg + (size_t)(i0 - 1) * B1 * Kp * plan->argw,
+                  a.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(uo.data(), plan->slots[slot].u_old + (size_t)(i0 - 1) * M, uo.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // 1-based tuple of every admissible level
+    std::vector<int64_t> tup((size_t)K * M);
+    for (int k = 0; k < K; ++k) {
+        int64_t rem = plan->grid_offset[k];
+        for (int m = 0; m < M; ++m) { tup[(size_t)k * M + m] = rem % plan->grid_dims[m] + 1; rem /= plan->grid_dims[m]; }
+    }
+    const size_t G = (size_t)plan->G;
+    for (size_t x = 0; x < rows * G * B1 * M; ++x) U_out[x] = fill;
+    const unsigned mark = plan->argw == 1 ? 0xffu : 0xffffu;
+    for (size_t r = 0; r < rows; ++r)
+        for (int k = 0; k < K; ++k) {
+            double bd = 0.;
+            for (int m = 0; m < M; ++m) bd += std::fabs((double)plan->level_values[(size_t)k * M + m] - uo[r * M + m]);
+            if (!(bd < (double)B1)) continue;
+            const size_t bt = (size_t)bd;
+            for (size_t bsrc = 0; bsrc + bt < B1; ++bsrc) {
+                const size_t cell = (r * B1 + bsrc) * Kp + k;
+                const unsigned v = plan->argw == 1 ? a[cell] : ((const uint16_t *)a.data())[cell];
+                if (v == mark || v >= (unsigned)K) continue;
+                int64_t *dst = U_out + M * ((bsrc + bt) + B1 * ((size_t)plan->grid_offset[k] + G * r));
+                for (int m = 0; m < M; ++m) dst[m] = tup[(size_t)v * M + m];
+            }
+        }
+    return BB200_OK;
+}
+
+int bb200_count_updates(bb200_plan *plan, int32_t slot, int64_t *n_updates)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    if (!n_updates) return fail(BB200_ERR_ARG, "n_updates is NULL");
+    Guard g(plan);
+    if (!plan->slots[slot].has_dp) return fail(BB200_ERR_STATE, "slot %d has no DP result yet", slot);
+    CU(cudaStreamSynchronize(plan->stream));
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, plan->slots[slot].n_updates, sizeof v, cudaMemcpyDeviceToHost));
+    *n_updates = (int64_t)v;
+    return BB200_OK;
+}
+
+int bb200_pred_integral(bb200_plan *plan, int32_t slot, double *int_val)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    if (!int_val) return fail(BB200_ERR_ARG, "int_val is NULL");
+    Guard g(plan);
+    launch_pred_integral(plan->tab, plan->slots_dev[slot], plan->d_scalar, plan->stream);
+    plan->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(plan->h_rec, plan->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    CU(cudaStreamSynchronize(plan->stream));
+    *int_val = plan->h_rec[0];
+    return BB200_OK;
+}
+
+int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv)
+{
+    int rc = check_slot(plan, slot);
+    if (rc) return rc;
+    if (!tv) return fail(BB200_ERR_ARG, "tv is NULL");
+    int mode;
+    if (std::isinf(p) && p > 0) mode = 0;
+    else if (p == 1.) mode = 1;
+    else if (p == 2.) mode = 2;
+    else return fail(BB200_ERR_ARG, "TV_p on the device supports p in {1, 2, Inf}; got %g", p);
+    Guard g(plan);
+    launch_tv(plan->tab, plan->slots_dev[slot], mode, plan->d_scalar, plan->stream);
+    plan->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(plan->h_rec, plan->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    CU(cudaStreamSynchronize(plan->stream));
+    *tv = plan->h_rec[0];
+    return BB200_OK;
+}
+
+int bb200_stats(bb200_plan *plan, double *out, int32_t count)
+{
+    if (!plan || !out) return fail(BB200_ERR_ARG, "bad arguments");
+    Guard g(plan);
+    const double v[10] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+                          plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
+                          (double)plan->argw, (double)plan->dev_bytes,
+                          plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.};
+    for (int k = 0; k < count && k < 10; ++k) out[k] = v[k];
+    return BB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// bb200_internal.cuh -- shared definitions of the B200 trust-region DP library (sm_100a only).
+//
+// Device data layout (all per plan unless "per slot"):
+//   lvd   double[K][M]    level values nu_k[m] as Float64 (HelpFunctions.jl:54-56 converts Int64->Float64)
+//   cost  double[K][Kp]   cost[j*Kp + l] jump cost successor j (stage i+1) <- level l (stage i); pad = +Inf
+//   goff  int64[K]        column-major grid offset of admissible tuple k
+//   per slot:
+//   df, u_old, u  double[nPad][M]   reference layout (Julia M x n), rows padded to the TMA chunk
+//   phi   double[2][B1][Kp]  exit state (S7): [0] = stage-1 values, [1] = stage-2 values, level fastest
+//   arg   ArgT[n-1][B1][Kp]  packed argmin, indexed by SOURCE budget row b' = b - b~_l(i):
+//                            arg[i-1][b'][l] = winner j of target cell (b' + b~_l(i), l) at stage i
+//                            (MARK where no candidate won, i.e. the reference wrote nothing)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bb200 {
+
+constexpr int kChunk = 64;        // stages per TMA chunk of df / u_old
+constexpr int kMaxWaveThreads = 256;  // wavefront CTA size cap: keeps 255 registers per thread available
+constexpr int kMaxM = 8;          // controls supported by the kernels
+constexpr int kFlagStride = 16;   // u64 words between per-CTA progress flags (128 B apart)
+constexpr int kHaloRing = 8;      // stages of halo kept in flight between neighbouring CTAs
+
+struct SlotDev {
+    const double *df;     // [nPad][M]
+    const double *u_old;  // [nPad][M]
+    double *u;            // [nPad][M]
+    double *phi;          // [2][B1][Kp]
+    void *arg;            // ArgT[n-1][B1][Kp]
+    unsigned long long *n_updates;  // exact relaxation count of the last DP
+    double *rec;          // [4] phi_star, b_star, k_star, status of the last selection
+};
+
+struct Tables {
+    int n, M, K, Kp, B1;  // B1 = B + 1
+    double dt;
+    const double *lvd;
+    const double *cost;
+    const long long *goff;
+};
+
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// Stage cost and budget use of level l at 0-based stage row `row` (S3):
+//   s = 0. + (dt*df[0])*nu[0] + (dt*df[1])*nu[1] + ..   every * and + rounded separately
+//   bt = sum_m Int64(|nu[m] - u_old[m]|), clamped to B1 (anything > B is unreachable)
+__device__ __forceinline__ void stage_cost(const Tables &t, const double *__restrict__ lv,
+                                           const double *__restrict__ dfrow,
+                                           const double *__restrict__ uorow, double &s, int &bt)
+{
+    double acc = 0.;
+    double b = 0.;
+#pragma unroll 1
+    for (int m = 0; m < t.M; ++m) {
+        const double nu = lv[m];
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(t.dt, dfrow[m]), nu));
+        b += fabs(nu - uorow[m]);
+    }
+    s = acc;
+    bt = (b < (double)t.B1) ? (int)b : t.B1;  // NaN compares false -> unreachable
+}
+
+// Julia findmin order (S8): isgreater(fm, fx) == "fx strictly precedes fm".
+__device__ __forceinline__ bool julia_isless(double a, double b)
+{
+    if (a != a) return false;
+    if (b != b) return true;
+    if (a < b) return true;
+    if (a == b) return (__double_as_longlong(a) < 0) && !(__double_as_longlong(b) < 0);
+    return false;
+}
+__device__ __forceinline__ bool julia_isgreater(double fm, double fx)
+{
+    return (fm != fm || fx != fx) ? julia_isless(fm, fx) : julia_isless(fx, fm);
+}
+
+}  // namespace bb200

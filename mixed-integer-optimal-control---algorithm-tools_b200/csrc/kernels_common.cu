@@ -1,0 +1,309 @@
+// kernels_common.cu -- prep / per-stage (validation path) / selection / backtrack kernels.
+//
+// Reference semantics ("Normative semantics" S1-S10) of
+//   bellman_TRM!  HelpFunctions.jl:20-83      eval_u_TRM!  HelpFunctions.jl:98-124
+#include "bb200_internal.cuh"
+#include "kernels.cuh"
+
+namespace bb200 {
+
+// ------------------------------------------------------------------------------------------------
+// prep: validates u_old (Julia's InexactError, HelpFunctions.jl:37,57), counts the exact number of
+// innermost-loop executions N, finds the largest budget use <= B (pipeline halo depth)
+// and resets the exit-state rows to +Inf (HelpFunctions.jl:27,47).
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_kernel(Tables t, SlotDev slot, int *err, int *btmax)
+{
+    __shared__ unsigned long long s_upd;
+    __shared__ int s_bad, s_max;
+    if (threadIdx.x == 0) { s_upd = 0ull; s_bad = 0; s_max = 0; }
+    __syncthreads();
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    const double inf = d_inf();
+    for (long long x = gtid; x < 2ll * t.B1 * t.Kp; x += nthr) slot.phi[x] = inf;
+    unsigned long long upd = 0ull;
+    int bad = 0, mx = 0;
+    for (long long row = gtid; row < t.n; row += nthr) {
+        const double *uo = slot.u_old + row * t.M;
+        for (int m = 0; m < t.M; ++m) {
+            const double v = uo[m];
+            if (!(fabs(v) <= 1073741824.0) || v != floor(v)) bad = 1;
+        }
+        long long reach = 0;
+        for (int l = 0; l < t.K; ++l) {
+            double b = 0.;
+            for (int m = 0; m < t.M; ++m) b += fabs(t.lvd[l * t.M + m] - uo[m]);
+            const int bt = (b < (double)t.B1) ? (int)b : t.B1;
+            if (bt < t.B1) { reach += t.B1 - bt; mx = max(mx, bt); }
+        }
+        if (row < t.n - 1) upd += (unsigned long long)reach * (unsigned long long)t.K;
+    }
+    atomicAdd(&s_upd, upd);
+    if (bad) atomicOr(&s_bad, 1);
+    atomicMax(&s_max, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_upd) atomicAdd(slot.n_updates, s_upd);
+        if (s_bad) atomicOr(&err[0], 1);
+        atomicMax(btmax, s_max);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Validation path: one launch per stage, value rows ping-pong in HBM.  Thread = (source row b', level l).
+//   terminal stage (HelpFunctions.jl:27-43): phi[t][l] = (t == b~_l(n)) ? s_l(n) : Inf
+//   stage i (HelpFunctions.jl:45-82): target (b'+b~_l, l) = min_j (s_l + c_jl) + phi_next[b'][j],
+//   strict '>' scan in iterator order, so the earliest j wins ties and Inf/NaN never win.
+// ------------------------------------------------------------------------------------------------
+__global__ void terminal_kernel(Tables t, SlotDev slot, int pslot)
+{
+    const int l = threadIdx.x;
+    const int b = blockIdx.x * blockDim.y + threadIdx.y;
+    if (l >= t.K || b >= t.B1) return;
+    const long long row = t.n - 1;
+    double s; int bt;
+    stage_cost(t, t.lvd + l * t.M, slot.df + row * t.M, slot.u_old + row * t.M, s, bt);
+    slot.phi[((long long)pslot * t.B1 + b) * t.Kp + l] = (b == bt) ? s : d_inf();
+}
+
+template <typename ArgT>
+__global__ void stage_kernel(Tables t, SlotDev slot, int i /* 1-based stage */)
+{
+    constexpr ArgT MARK = (ArgT)~(ArgT)0;
+    const int l = threadIdx.x;
+    const int bsrc = blockIdx.x * blockDim.y + threadIdx.y;
+    if (l >= t.K || bsrc >= t.B1) return;
+    const int cur = (i + 1) & 1, nxt = i & 1;  // slot(i) = (i+1)%2 0-based, slot(i+1) = i%2
+    const long long row = i - 1;
+    double s; int bt;
+    stage_cost(t, t.lvd + l * t.M, slot.df + row * t.M, slot.u_old + row * t.M, s, bt);
+    double *pc = slot.phi + (long long)cur * t.B1 * t.Kp;
+    const double *pn = slot.phi + ((long long)nxt * t.B1 + bsrc) * t.Kp;
+    if (bsrc < bt) pc[(long long)bsrc * t.Kp + l] = d_inf();  // target rows nobody reaches (:47)
+    const int tgt = bsrc + bt;
+    if (tgt >= t.B1) return;  // outside `for b = 0:B-b~` (:69)
+    double best = d_inf();
+    int arg = (int)MARK;
+    for (int j = 0; j < t.K; ++j) {
+        const double a = __dadd_rn(s, t.cost[j * t.Kp + l]);  // :67
+        const double v = __dadd_rn(a, pn[j]);                 // :71
+        if (best > v) { best = v; arg = j; }                  // :73-76
+    }
+    pc[(long long)tgt * t.Kp + l] = best;
+    reinterpret_cast<ArgT *>(slot.arg)[((long long)(i - 1) * t.B1 + bsrc) * t.Kp + l] = (ArgT)arg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Selection (HelpFunctions.jl:102-112): argmin over phi[0][0..Bnew][*] in the reference's column-major
+// order (budget fastest, then grid offset) with Julia 1.10 findmin semantics (S8).  One CTA; per-thread
+// scan, warp-shuffle reduction, then across warps through shared memory.
+// ------------------------------------------------------------------------------------------------
+struct Cand { double v; long long pos; int k; int b; };
+
+__device__ __forceinline__ bool cand_precedes(const Cand &x, const Cand &y)
+{
+    if (julia_isgreater(y.v, x.v)) return true;
+    if (julia_isgreater(x.v, y.v)) return false;
+    return x.pos < y.pos;
+}
+
+__global__ void select_kernel(Tables t, SlotDev slot, int Bnew, int *err)
+{
+    __shared__ Cand s_c[32];
+    Cand best;
+    best.v = d_inf(); best.pos = 0x7fffffffffffffffLL; best.k = -1; best.b = -1;
+    const long long cells = (long long)(Bnew + 1) * t.K;
+    for (long long x = threadIdx.x; x < cells; x += blockDim.x) {
+        const int b = (int)(x / t.K), k = (int)(x % t.K);
+        Cand c;
+        c.v = slot.phi[(long long)b * t.Kp + k];
+        c.pos = t.goff[k] * (long long)t.B1 + b;
+        c.k = k; c.b = b;
+        if (cand_precedes(c, best)) best = c;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        Cand o;
+        o.v = __shfl_down_sync(0xffffffffu, best.v, off);
+        o.pos = __shfl_down_sync(0xffffffffu, best.pos, off);
+        o.k = __shfl_down_sync(0xffffffffu, best.k, off);
+        o.b = __shfl_down_sync(0xffffffffu, best.b, off);
+        if (cand_precedes(o, best)) best = o;
+    }
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        Cand c = s_c[threadIdx.x < nw ? threadIdx.x : 0];
+        for (int off = 16; off > 0; off >>= 1) {
+            Cand o;
+            o.v = __shfl_down_sync(0xffffffffu, c.v, off);
+            o.pos = __shfl_down_sync(0xffffffffu, c.pos, off);
+            o.k = __shfl_down_sync(0xffffffffu, c.k, off);
+            o.b = __shfl_down_sync(0xffffffffu, c.b, off);
+            if (cand_precedes(o, c)) c = o;
+        }
+        if (threadIdx.x == 0) {
+            slot.rec[0] = c.v;
+            slot.rec[1] = (double)c.b;
+            slot.rec[2] = (double)c.k;
+            // +Inf selected: no feasible trajectory; the reference would go on to read stale U.
+            const bool stale = (c.k < 0) || (c.v == d_inf());
+            slot.rec[3] = stale ? 1. : 0.;
+            if (stale) atomicOr(&err[1], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backtrack (HelpFunctions.jl:108-122): a dependent chase of n-1 argmin bytes.  With the source-row
+// indexed table one step is  b' = b - b~_l(i);  l <- arg[i-1][b'][l];  b <- b'.
+// One warp: lane 0 chases; all lanes prefetch the next rows' neighbourhood into L2/L1.
+// ------------------------------------------------------------------------------------------------
+template <typename ArgT>
+__global__ void backtrack_kernel(Tables t, SlotDev slot, int *err)
+{
+    constexpr ArgT MARK = (ArgT)~(ArgT)0;
+    if (slot.rec[3] != 0.) return;
+    if (threadIdx.x != 0) return;
+    int b = (int)slot.rec[1];
+    int l = (int)slot.rec[2];
+    const ArgT *arg = reinterpret_cast<const ArgT *>(slot.arg);
+    for (int m = 0; m < t.M; ++m) slot.u[m] = t.lvd[l * t.M + m];
+    for (long long i = 1; i <= t.n - 1; ++i) {
+        const double *uo = slot.u_old + (i - 1) * t.M;
+        double d = 0.;
+        for (int m = 0; m < t.M; ++m) d += fabs(t.lvd[l * t.M + m] - uo[m]);
+        const int bsrc = b - (int)d;
+        if (bsrc < 0) { atomicOr(&err[1], 1); slot.rec[3] = 1.; return; }
+        const ArgT a = arg[((i - 1) * t.B1 + bsrc) * t.Kp + l];
+        if (a == MARK || (int)a >= t.K) { atomicOr(&err[1], 1); slot.rec[3] = 1.; return; }
+        l = (int)a;
+        b = bsrc;
+        for (int m = 0; m < t.M; ++m) slot.u[i * t.M + m] = t.lvd[l * t.M + m];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// "Next" rows: sequential-order reductions on the resident arrays.
+//   N1  int_val = dt * sum_j df[:,j]'(u_old[:,j]-u[:,j])   multi-trust.jl:117-121
+//   N3  TV_p(u,p), p in {Inf, 1, 2}                           HelpFunctions.jl:251-268
+// The floating-point sums are order dependent, so one thread accumulates in the reference's order while
+// the CTA stages the operands through shared memory in coalesced chunks.
+// ------------------------------------------------------------------------------------------------
+__global__ void pred_integral_kernel(Tables t, SlotDev slot, double *out)
+{
+    extern __shared__ double sh[];
+    double *term = sh;  // [chunk]
+    const int chunk = blockDim.x;
+    double acc = 0.;
+    for (long long j0 = 0; j0 < t.n; j0 += chunk) {
+        const long long j = j0 + threadIdx.x;
+        if (j < t.n) {
+            double dot = 0.;
+            for (int m = 0; m < t.M; ++m) {
+                const double x = __dmul_rn(slot.df[j * t.M + m],
+                                           __dsub_rn(slot.u_old[j * t.M + m], slot.u[j * t.M + m]));
+                dot = (m == 0) ? x : __dadd_rn(dot, x);
+            }
+            term[threadIdx.x] = dot;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int cnt = (int)min((long long)chunk, t.n - j0);
+            for (int k = 0; k < cnt; ++k) acc = __dadd_rn(acc, term[k]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = __dmul_rn(acc, t.dt);
+}
+
+__global__ void tv_kernel(Tables t, SlotDev slot, int mode /*0 = Inf, 1, 2*/, double *out)
+{
+    extern __shared__ double sh[];
+    double *term = sh;
+    const int chunk = blockDim.x;
+    double acc = 0.;
+    for (long long i0 = 1; i0 < t.n; i0 += chunk) {
+        const long long i = i0 + threadIdx.x;
+        if (i < t.n) {
+            double v = 0.;
+            if (mode == 0) {
+                v = -d_inf();
+                for (int m = 0; m < t.M; ++m) {
+                    const double d = fabs(__dsub_rn(slot.u[i * t.M + m], slot.u[(i - 1) * t.M + m]));
+                    if (d > v || d != d) v = d;
+                }
+            } else {
+                for (int m = 0; m < t.M; ++m) {
+                    const double d = fabs(__dsub_rn(slot.u[i * t.M + m], slot.u[(i - 1) * t.M + m]));
+                    const double pw = (mode == 1) ? d : __dmul_rn(d, d);
+                    v = (m == 0) ? pw : __dadd_rn(v, pw);
+                }
+                if (mode == 2) v = sqrt(v);  // integer-valued u: exact when the sum is a perfect square
+            }
+            term[threadIdx.x] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int cnt = (int)min((long long)chunk, t.n - i0);
+            for (int k = 0; k < cnt; ++k) acc = __dadd_rn(acc, term[k]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = acc;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+void launch_prep(const Tables &t, const SlotDev &slot, int *err, int *btmax, cudaStream_t st)
+{
+    const int threads = 256;
+    long long work = t.n > 2ll * t.B1 * t.Kp / 64 ? t.n : 2ll * t.B1 * t.Kp / 64;
+    int blocks = (int)((work + threads - 1) / threads);
+    if (blocks > 592) blocks = 592;
+    if (blocks < 1) blocks = 1;
+    prep_kernel<<<blocks, threads, 0, st>>>(t, slot, err, btmax);
+}
+
+int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream_t st)
+{
+    // blockDim.x = levels rounded to a warp, blockDim.y = source rows
+    int bx = ((t.K + 31) / 32) * 32;
+    if (bx > 1024) return -1;
+    int by = 1024 / bx;
+    if (by > 8) by = 8;
+    dim3 block(bx, by);
+    dim3 grid((t.B1 + by - 1) / by);
+    int launches = 0;
+    terminal_kernel<<<grid, block, 0, st>>>(t, slot, (t.n + 1) & 1);
+    ++launches;
+    for (int i = t.n - 1; i >= 1; --i) {
+        if (argw == 1) stage_kernel<uint8_t><<<grid, block, 0, st>>>(t, slot, i);
+        else stage_kernel<uint16_t><<<grid, block, 0, st>>>(t, slot, i);
+        ++launches;
+    }
+    return launches;
+}
+
+void launch_select(const Tables &t, const SlotDev &slot, int Bnew, int *err, cudaStream_t st)
+{
+    select_kernel<<<1, 1024, 0, st>>>(t, slot, Bnew, err);
+}
+
+void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st)
+{
+    if (argw == 1) backtrack_kernel<uint8_t><<<1, 32, 0, st>>>(t, slot, err);
+    else backtrack_kernel<uint16_t><<<1, 32, 0, st>>>(t, slot, err);
+}
+
+void launch_pred_integral(const Tables &t, const SlotDev &slot, double *out, cudaStream_t st)
+{
+    pred_integral_kernel<<<1, 1024, 1024 * sizeof(double), st>>>(t, slot, out);
+}
+
+void launch_tv(const Tables &t, const SlotDev &slot, int mode, double *out, cudaStream_t st)
+{
+    tv_kernel<<<1, 1024, 1024 * sizeof(double), st>>>(t, slot, mode, out);
+}
+
+}  // namespace bb200
