@@ -48,7 +48,6 @@ extern "C" {
 /* plan flags */
 #define BB200_FLAG_STAGE_KERNELS 1u /* force the one-launch-per-stage kernels (validation path)    */
 #define BB200_FLAG_NO_GRAPH 2u      /* do not capture TR iterations into a CUDA graph              */
-#define BB200_FLAG_KEEP_ALL_PHI 4u  /* debug: keep every stage's value rows (tests only, small n)  */
 
 typedef struct bb200_plan bb200_plan;
 
@@ -164,8 +163,14 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *   4 CTAs used by the last DP launch          5 source rows per CTA
  *   6 argmin bytes per cell (1 or 2)           7 device bytes owned by the plan
  *   8 threads per CTA of the last DP launch    9 j-split of the last DP launch
+ *  10 device time [ms] of the last persistent wavefront kernel alone (events around that launch)
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);
+
+/* FP64-pipe issue-rate microbenchmark on `device` (the roofline denominator; MEASURED_PEAKS.json has no
+ * FP64 figure).  mode 0: independent DADD chains; mode 1: DADD + DSETP + selects (the relaxation's mix,
+ * counted as 2 FP64 ops).  Runs a full-chip kernel for about target_ms; returns lane-operations per second. */
+int bb200_fp64_peak(int device, int32_t mode, double target_ms, double *ops_per_s, double *elapsed_ms);
 
 /* Tuning knobs for experiments (0 = automatic): number of CTAs, j-split, rows per thread. */
 int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t variant);

@@ -158,14 +158,22 @@ class TRMPlan:
         return v.value
 
     def stats(self):
-        out = np.zeros(10, dtype=np.float64)
-        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 10))
+        out = np.zeros(11, dtype=np.float64)
+        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 11))
         keys = ("dp_ms", "backtrack_ms", "launches", "path", "ctas", "rows_per_cta", "arg_bytes",
-                "device_bytes", "threads", "jsplit")
+                "device_bytes", "threads", "jsplit", "wave_ms")
         return dict(zip(keys, out.tolist()))
 
     def close(self):
         self._fin()
+
+
+def fp64_peak(device=0, mode=0, target_ms=300.0):
+    """FP64-pipe issue rate of `device` in lane-operations per second (roofline denominator)."""
+    lib = _lib.load()
+    ops, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib.bb200_fp64_peak(int(device), int(mode), float(target_ms), ctypes.byref(ops), ctypes.byref(ms)))
+    return ops.value, ms.value
 
 
 # ---- drop-in free functions (one plan per U array, like the Julia glue's objectid(U) key) -----------

@@ -74,7 +74,7 @@ struct bb200_plan {
     std::vector<SlotHost> slots;
     std::vector<SlotDev> slots_dev;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // pinned staging
     double *h_rec = nullptr;
     int *h_err = nullptr;
@@ -85,7 +85,7 @@ struct bb200_plan {
     WaveCfg cfg{};
     int tune_ctas = 0, tune_js = 0, tune_variant = 0;
     // stats
-    double last_dp_ms = 0., last_bt_ms = 0.;
+    double last_dp_ms = 0., last_bt_ms = 0., last_wave_ms = 0.;
     double launches = 0.;
     int last_path = -1;
     size_t dev_bytes = 0;
@@ -160,7 +160,9 @@ int queue_dp(bb200_plan *p, int slot0, int count)
         c.flags = p->d_flags;
         c.err = p->d_err;
         c.btmax = p->d_btmax;
+        CU(cudaEventRecord(p->ev[4], st));
         CU(launch_wavefront(p->tab, c, p->argw, st));
+        CU(cudaEventRecord(p->ev[5], st));
         p->launches += 1;
         p->last_path = 1;
     } else {
@@ -185,6 +187,7 @@ int queue_backtrack(bb200_plan *p, int slot, int64_t B_new, int rec_idx)
     SlotDev sd = p->slots_dev[slot];
     sd.rec = p->slots[slot].rec + 4 * rec_idx;
     CU(cudaEventRecord(p->ev[2], st));
+    CU(cudaMemsetAsync(p->d_err + 1, 0, sizeof(int), st));  // the stale flag is per selection
     launch_select(p->tab, sd, (int)B_new, p->d_err, st);
     launch_backtrack(p->tab, sd, p->argw, p->d_err, st);
     p->launches += 2;
@@ -202,6 +205,7 @@ int sync_and_check(bb200_plan *p)
     if (p->dp_timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->last_dp_ms = ms;
+        if (p->last_path == 1 && cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]) == cudaSuccess) p->last_wave_ms = ms;
         p->dp_timed = false;
     }
     if (p->bt_timed) {
@@ -645,15 +649,27 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv)
     return BB200_OK;
 }
 
+int bb200_fp64_peak(int device, int32_t mode, double target_ms, double *ops_per_s, double *elapsed_ms)
+{
+    if (!ops_per_s || !elapsed_ms || mode < 0 || mode > 1) return fail(BB200_ERR_ARG, "bad arguments");
+    if (bb200_device_count() == 0) return fail(BB200_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    CU(measure_fp64_rate(mode, prop.multiProcessorCount, target_ms, ops_per_s, elapsed_ms, 0));
+    return BB200_OK;
+}
+
 int bb200_stats(bb200_plan *plan, double *out, int32_t count)
 {
     if (!plan || !out) return fail(BB200_ERR_ARG, "bad arguments");
     Guard g(plan);
-    const double v[10] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+    const double v[11] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
                           plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
                           (double)plan->argw, (double)plan->dev_bytes,
-                          plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.};
-    for (int k = 0; k < count && k < 10; ++k) out[k] = v[k];
+                          plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.,
+                          plan->last_wave_ms};
+    for (int k = 0; k < count && k < 11; ++k) out[k] = v[k];
     return BB200_OK;
 }
 

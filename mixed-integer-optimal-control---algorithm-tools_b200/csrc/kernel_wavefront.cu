@@ -74,7 +74,7 @@ __device__ __forceinline__ void st_release(unsigned long long *p, unsigned long 
 }
 
 // Spin until *flag >= want.  A bounded watchdog turns a lost dependency into an error code instead of a
-// hung GPU: after ~2^28 polls the CTA raises the abort flag and every poller gives up.
+// hung GPU: after ~2^24 polls the CTA raises the abort flag and every poller gives up.
 __device__ __forceinline__ void wait_flag(const unsigned long long *flag, long long want, int *err)
 {
     if (want <= 0) return;
@@ -82,7 +82,7 @@ __device__ __forceinline__ void wait_flag(const unsigned long long *flag, long l
     while ((long long)ld_acquire(flag) < want) {
         if ((++spins & 0x3ffu) == 0) {
             if (*(volatile int *)&err[3]) return;
-            if (spins > (1u << 28)) {
+            if (spins > (1u << 24)) {
                 atomicOr(&err[2], 1);
                 atomicOr(&err[3], 1);
                 return;

@@ -40,4 +40,8 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     int want_js, int want_variant, WaveCfg &cfg);
 cudaError_t launch_wavefront(const Tables &t, const WaveCfg &cfg, int argw, cudaStream_t st);
 
+// kernels_microbench.cu
+cudaError_t measure_fp64_rate(int mode, int num_sms, double target_ms, double *ops_per_s, double *elapsed_ms,
+                              cudaStream_t st);
+
 }  // namespace bb200

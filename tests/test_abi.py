@@ -1,0 +1,69 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every symbol include/*.h declares,
+the ctypes table covers exactly that set, and compute entry points fail loudly without a GPU."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(bb200_[a-z_0-9]+)\s*\(", src))
+    return names
+
+
+@pytest.fixture(scope="module")
+def built(mioc):
+    import __graft_entry__ as g
+    g.build()
+    return mioc
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = ctypes.CDLL(built._lib.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 20
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/bellman_b200.h but not exported"
+    assert set(built._lib.SIGNATURES) == decl
+
+
+def test_version_and_error_string(built):
+    lib = built._lib.load()
+    assert lib.bb200_version() >= 1000
+    assert isinstance(lib.bb200_last_error(), bytes)
+
+
+def test_argument_validation_needs_no_gpu(built):
+    lib = built._lib.load()
+    h = built._lib.c_plan_p()
+    rc = lib.bb200_plan_create(0, 0, 1, 1, 1, None, None, None, None, 1.0, 1, 0, ctypes.byref(h))
+    assert rc == built._lib.ERR_ARG and not h.value
+    assert lib.bb200_sync(None) == built._lib.ERR_ARG
+
+
+def test_best_candidate_host_reduction(built):
+    lib = built._lib.load()
+    vals = np.array([3.0, -1.5, np.nan, -1.5, 7.0])
+    idx = np.array([10, 42, 5, 17, 1], dtype=np.int64)
+    bv, bi = ctypes.c_double(), ctypes.c_int64()
+    assert lib.bb200_best_candidate(built._lib.f64p(vals), built._lib.i64p(idx), 5, ctypes.byref(bv), ctypes.byref(bi)) == 0
+    assert (bv.value, bi.value) == (-1.5, 17)  # ties go to the smallest global index, NaN never wins
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="box has a GPU")
+def test_no_cpu_fallback(built):
+    assert built.device_count() == 0
+    with pytest.raises(built.BellmanB200Error, match="no CPU fallback"):
+        built.TRMPlan([[0, 1]], built.product_iterator([[0, 1]]), 4, 2, 0.5, 1, 1.0)
+    with pytest.raises(built.BellmanB200Error):
+        built.bellman_TRM(np.zeros((4, 1)), np.zeros((4, 1)), 2, 0.5, 1, 1.0, [[0, 1]], None, np.zeros((2, 2, 3)),
+                          built.product_iterator([[0, 1]]))

@@ -1,0 +1,309 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, must be
+BIT-EXACT against the CPU oracle -- same value table (both slots), same argmin on every cell the DP wrote,
+same control trajectory for every trial radius -- on the known-answer tests, the committed golden vectors,
+tie-heavy and random instances of every example shape, and through size-independent properties at the
+full BASELINE size."""
+import importlib
+
+import numpy as np
+import pytest
+
+from helpers import inf_list, kat_iterator, load_kats, load_seeded, objective_of, phi_admissible, random_instance
+
+pytestmark = pytest.mark.gpu
+
+PATHS = [pytest.param(0, id="wavefront"), pytest.param(1, id="stage-kernels")]
+
+
+def oracle_tables(o, nu, it, n, B, df, u_old, beta, p, dt, cost):
+    U, Phi = o.alloc_tables(nu, n, B)
+    n_upd = o.bellman_TRM(df, u_old, B, beta, p, dt, nu, U, Phi, it, cost=cost, threads=True)
+    return U, Phi, n_upd
+
+
+def check_against_oracle(m, o, nu, it, n, B, df, u_old, beta, p, dt, flags, radii=None, tune=None):
+    plan = m.TRMPlan(nu, it, n, B, beta, p, dt, flags=flags)
+    if tune:
+        plan.tune(**tune)
+    plan.bellman(df, u_old)
+    U, Phi, n_upd = oracle_tables(o, nu, it, n, B, df, u_old, beta, p, dt, plan.cost)
+    got_phi = plan.export_phi()
+    if n == 1:
+        # the reference never touches slot 2 for n == 1 (it keeps the caller's zeros); the device reports +Inf
+        np.testing.assert_array_equal(got_phi[0], Phi[0])
+    else:
+        np.testing.assert_array_equal(got_phi, Phi)                  # bit-exact incl. +Inf cells
+    assert plan.count_updates() == n_upd
+    if n > 1:
+        # every cell the reference wrote must hold the same index tuple; unwritten cells are `fill`
+        ref = U.copy()
+        got = plan.export_argmin(1, n, fill=0)
+        np.testing.assert_array_equal(got, ref)
+    for Bn in (radii if radii is not None else sorted({B, B // 2, B // 3, 1 if B >= 1 else 0, 0}, reverse=True)):
+        u = np.zeros((n, len(nu)))
+        u_ref = np.zeros((n, len(nu)))
+        info = {}
+        ps, bs, ks = plan.eval_u(u, Bn)
+        o.eval_u_TRM(u_ref, u_old, U, Phi, Bn, nu, info=info)
+        np.testing.assert_array_equal(u, u_ref)
+        assert (ps, bs, int(plan.grid_offset[ks])) == (info["phi_star"], info["b_star"], info["g_star"])
+    st = plan.stats()
+    assert int(st["path"]) == (0 if flags & 1 else 1), "the requested kernel path did not run"
+    plan.close()
+    return st
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("name", ["KAT-1", "KAT-2"])
+def test_known_answers(gpu_lib, oracle, name, flags):
+    m, o = gpu_lib, oracle
+    kat = load_kats()[name]
+    it = kat_iterator(o, kat)
+    df, u_old = np.array(kat["df"]), np.array(kat["u_old"])
+    plan = m.TRMPlan(kat["nu"], it, kat["n"], kat["B"], kat["beta"], kat["p"], kat["dt"], flags=flags)
+    plan.bellman(df, u_old)
+    pa = phi_admissible(o, plan.export_phi(), kat["nu"], it)
+    np.testing.assert_array_equal(pa[0], inf_list(kat["phi_slot1"]))
+    np.testing.assert_array_equal(pa[1], inf_list(kat["phi_slot2"]))
+    g = o.grid_offsets(kat["nu"], it)
+    Ur = plan.export_argmin(1, kat["n"], fill=0).reshape(kat["n"] - 1, -1, kat["B"] + 1, len(kat["nu"]))
+    for i, b, k, tup in kat["U"]:
+        assert Ur[i - 1, g[k], b].tolist() == tup
+    for Bn, exp in kat["select"].items():
+        u = np.zeros_like(u_old)
+        ps, bs, ks = plan.eval_u(u, int(Bn))
+        assert (ps, bs, ks) == (exp["phi"], exp["b"], exp["k"])
+        np.testing.assert_array_equal(u, u_old if exp["u"] == "u_old" else np.array(exp["u"]))
+    plan.close()
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_committed_golden_vectors(gpu_lib, flags):
+    m = gpu_lib
+    for name, c in load_seeded().items():
+        meta = c["meta"]
+        plan = m.TRMPlan(meta["nu"], meta["iterator"], meta["n"], meta["B"], meta["beta"], meta["p"], meta["dt"],
+                         flags=flags, cost=c["cost"])
+        plan.bellman(c["df"], c["u_old"])
+        np.testing.assert_array_equal(plan.export_phi(), c["Phi"], err_msg=name)
+        assert plan.count_updates() == int(c["n_updates"][0])
+        for r, u_exp in zip(c["radii"], c["u"]):
+            u = np.zeros_like(c["u_old"])
+            plan.eval_u(u, int(r))
+            np.testing.assert_array_equal(u, u_exp, err_msg=f"{name} B'={r}")
+        plan.close()
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("tie_heavy", [False, True])
+def test_random_small_instances(gpu_lib, oracle, flags, tie_heavy):
+    rng = np.random.default_rng(2024 + int(tie_heavy))
+    for _ in range(40):
+        inst = random_instance(rng, oracle, tie_heavy=tie_heavy, n_max=12, B_max=14)
+        check_against_oracle(gpu_lib, oracle, inst["nu"], inst["it"], inst["n"], inst["B"], inst["df"], inst["u_old"],
+                             inst["beta"], inst["p"], inst["dt"], flags,
+                             radii=list(range(inst["B"], -1, -1)))
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("kind,n,tie", [("fishing", 1024, False), ("vanderpol", 1024, True), ("doubletank", 1024, False),
+                                        ("convolution", 1024, True), ("heat", 256, True), ("heat", 1024, False)])
+def test_example_shapes(gpu_lib, oracle, kind, n, tie, flags):
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.example_shaped(kind, n=n, seed=31, tie_heavy=tie)
+    check_against_oracle(gpu_lib, oracle, inst.nu, inst.iterator, inst.n, inst.B, inst.df, inst.u_old, inst.beta,
+                         inst.p, inst.dt, flags)
+
+
+@pytest.mark.parametrize("tie", [False, True])
+def test_synthetic_config4_shape_vs_oracle(gpu_lib, oracle, tie):
+    """BASELINE config 4 (K=125, B=999) at an n the oracle finishes in seconds, bit for bit."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.synthetic(n=160, B=999, seed=20251018, tie_heavy=tie)
+    st = check_against_oracle(gpu_lib, oracle, inst.nu, inst.iterator, inst.n, inst.B, inst.df, inst.u_old, inst.beta,
+                              inst.p, inst.dt, 0, radii=[999, 499, 249, 124, 0])
+    assert st["ctas"] >= 100  # the pipelined path really spreads over the GPU
+
+
+@pytest.mark.parametrize("tune", [dict(ctas=8, jsplit=1), dict(ctas=5, jsplit=2), dict(ctas=16, jsplit=5, variant=2),
+                                  dict(ctas=40, jsplit=3, variant=4), dict(ctas=148, jsplit=8, variant=1),
+                                  dict(jsplit=1, variant=6), dict(ctas=9, variant=3)])
+def test_wavefront_geometries(gpu_lib, oracle, tune):
+    """Every tile variant / CTA count / j-split of the pipelined kernel gives identical bits."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.synthetic(n=70, B=211, seed=77, levels=4, M=3, tie_heavy=True)   # K = 64
+    check_against_oracle(gpu_lib, oracle, inst.nu, inst.iterator, inst.n, inst.B, inst.df, inst.u_old, inst.beta,
+                         inst.p, inst.dt, 0, tune=tune)
+
+
+def test_large_budget_use_spans_many_slices(gpu_lib, oracle):
+    """u_old far from most levels: pushes cross several CTA slices (halo depth D > 1)."""
+    nu = [[0, 5, 10, 15]] * 2
+    it = oracle.product_iterator(nu)
+    rng = np.random.default_rng(3)
+    n, B = 50, 120
+    lv = oracle.level_values(nu, it)
+    u_old = lv[rng.integers(0, len(it), size=n)].astype(np.float64)
+    df = np.round(rng.standard_normal((n, 2)) * 4) / 4
+    check_against_oracle(gpu_lib, oracle, nu, it, n, B, df, u_old, 0.25, 1, 0.5, 0, tune=dict(ctas=60))
+
+
+def test_n_equals_one_and_two(gpu_lib, oracle):
+    nu = [[0, 1, 2]]
+    it = oracle.product_iterator(nu)
+    for n in (1, 2, 3):
+        for flags in (0, 1):
+            df = np.arange(1, n + 1, dtype=np.float64).reshape(n, 1) * -0.5
+            u_old = np.ones((n, 1))
+            plan = gpu_lib.TRMPlan(nu, it, n, 2, 0.25, 1, 1.0, flags=flags)
+            plan.bellman(df, u_old)
+            U, Phi, _ = oracle_tables(oracle, nu, it, n, 2, df, u_old, 0.25, 1, 1.0, plan.cost)
+            got = plan.export_phi()
+            # for n == 1 the reference never touches slot 2 (zeros from the allocation); compare slot 1 only
+            np.testing.assert_array_equal(got[0], Phi[0])
+            if n > 1:
+                np.testing.assert_array_equal(got[1], Phi[1])
+            u, u_ref = np.zeros((n, 1)), np.zeros((n, 1))
+            plan.eval_u(u, 2)
+            oracle.eval_u_TRM(u_ref, u_old, U, Phi, 2, nu)
+            np.testing.assert_array_equal(u, u_ref)
+            plan.close()
+
+
+def test_error_behaviour(gpu_lib):
+    m = gpu_lib
+    nu = [[0, 1]]
+    it = m.product_iterator(nu)
+    plan = m.TRMPlan(nu, it, 4, 2, 0.5, 1, 1.0)
+    with pytest.raises(m.BellmanB200Error):          # backtrack before any DP
+        plan.eval_u(np.zeros((4, 1)))
+    with pytest.raises(m.InexactError):              # Julia: InexactError at HelpFunctions.jl:37,57
+        plan.bellman(np.zeros((4, 1)), np.array([[0.0], [0.5], [1.0], [0.0]]))
+    with pytest.raises(m.InexactError):
+        plan.bellman(np.zeros((4, 1)), np.array([[0.0], [np.nan], [1.0], [0.0]]))
+    plan.bellman(np.zeros((4, 1)), np.zeros((4, 1)))
+    with pytest.raises(m.BellmanB200Error):          # B_new > B
+        plan.eval_u(np.zeros((4, 1)), 3)
+    with pytest.raises(ValueError):
+        plan.bellman(np.zeros((5, 1)), np.zeros((5, 1)))
+    # inadmissible start (no level within the budget): the reference would read stale U
+    with pytest.raises(m.StaleCellError):
+        plan.bellman(np.zeros((4, 1)), np.full((4, 1), 9.0))
+        plan.eval_u(np.zeros((4, 1)), 2)
+    plan.close()
+
+
+def test_drop_in_functions_and_write_back(gpu_lib, oracle):
+    """bellman_TRM / eval_u_TRM with the reference's signatures, including filling the caller's U and Phi."""
+    m, o = gpu_lib, oracle
+    rng = np.random.default_rng(8)
+    inst = random_instance(rng, o, tie_heavy=True, K_choice=36, n_max=9, B_max=9)
+    inst["n"] = 9
+    lv = o.level_values(inst["nu"], inst["it"])
+    inst["u_old"] = lv[rng.integers(0, 36, size=9)].astype(np.float64)
+    inst["df"] = np.round(rng.standard_normal((9, 2)) * 4) / 4
+    U, Phi = o.alloc_tables(inst["nu"], 9, inst["B"])
+    Ur, Phir = o.alloc_tables(inst["nu"], 9, inst["B"])
+    m.bellman_TRM(inst["df"], inst["u_old"], inst["B"], inst["beta"], inst["p"], inst["dt"], inst["nu"], U, Phi,
+                  inst["it"], write_back=True)
+    o.bellman_TRM(inst["df"], inst["u_old"], inst["B"], inst["beta"], inst["p"], inst["dt"], inst["nu"], Ur, Phir,
+                  inst["it"])
+    np.testing.assert_array_equal(Phi, Phir)
+    np.testing.assert_array_equal(U, Ur)
+    u, ur = np.zeros((9, 2)), np.zeros((9, 2))
+    m.eval_u_TRM(u, inst["u_old"], U, Phi, inst["B"], inst["nu"])
+    o.eval_u_TRM(ur, inst["u_old"], Ur, Phir, inst["B"], inst["nu"])
+    np.testing.assert_array_equal(u, ur)
+
+
+def test_repeated_iterations_reuse_the_plan(gpu_lib, oracle):
+    """multi-trust.jl:105-114 call protocol: one DP per outer iteration, several shrinking radii, same tables."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.example_shaped("heat", n=128, seed=5, tie_heavy=True)
+    plan = gpu_lib.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt)
+    rng = np.random.default_rng(0)
+    u_old = inst.u_old.copy()
+    for it in range(4):
+        df = np.round(rng.standard_normal(inst.df.shape) * 4) / 4
+        U, Phi, _ = oracle_tables(oracle, inst.nu, inst.iterator, inst.n, inst.B, df, u_old, inst.beta, inst.p, inst.dt,
+                                  plan.cost)
+        u_first = np.zeros_like(u_old)
+        ps, bs, ks = plan.solve(df, u_old, u_first)
+        for Bn in (inst.B, inst.B // 2, inst.B // 4):
+            u, ur = np.zeros_like(u_old), np.zeros_like(u_old)
+            plan.eval_u(u, Bn)
+            oracle.eval_u_TRM(ur, u_old, U, Phi, Bn, inst.nu)
+            np.testing.assert_array_equal(u, ur)
+            if Bn == inst.B:
+                np.testing.assert_array_equal(u_first, ur)
+        u_old = ur.copy()
+    plan.close()
+
+
+def test_batched_subproblems_and_radius_sweep(gpu_lib, oracle):
+    """BASELINE config 5 in miniature: S subproblems x 4 radii, waves of `batch` slots."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    S, n, B = 7, 60, 99
+    insts = [wl.synthetic(n=n, B=B, seed=20251018 + 2 * s, levels=3, M=3, tie_heavy=(s % 2 == 0)) for s in range(S)]
+    base = insts[0]
+    plan = gpu_lib.TRMPlan(base.nu, base.iterator, n, B, 0.25, 1, base.dt, batch=3)
+    radii = [99, 49, 24, 12]
+    u_all, phi, bs, ks = plan.solve_batched(np.stack([i.df for i in insts]), np.stack([i.u_old for i in insts]), radii)
+    for s, inst in enumerate(insts):
+        U, Phi, _ = oracle_tables(oracle, inst.nu, inst.iterator, n, B, inst.df, inst.u_old, 0.25, 1, inst.dt, plan.cost)
+        for r, Bn in enumerate(radii):
+            ur = np.zeros((n, 3))
+            info = {}
+            oracle.eval_u_TRM(ur, inst.u_old, U, Phi, Bn, inst.nu, info=info)
+            np.testing.assert_array_equal(u_all[s, r], ur)
+            assert phi[s, r] == info["phi_star"] and bs[s, r] == info["b_star"]
+    plan.close()
+
+
+def test_next_rows_pred_integral_and_tv(gpu_lib, oracle):
+    """SURVEY 8f N1/N3 on the resident arrays."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.example_shaped("heat", n=300, seed=9)
+    plan = gpu_lib.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt)
+    u = np.zeros_like(inst.u_old)
+    plan.solve(inst.df, inst.u_old, u)
+    assert plan.pred_integral() == oracle.pred_integral(inst.df, inst.u_old, u, inst.dt)
+    assert plan.tv(1) == oracle.TV_p(u, 1)
+    assert plan.tv(float("inf")) == oracle.TV_p(u, float("inf"))
+    assert abs(plan.tv(2) - oracle.TV_p(u, 2)) <= 1e-12 * max(1.0, oracle.TV_p(u, 2))
+    plan.close()
+
+
+def test_full_size_properties(gpu_lib, oracle):
+    """BASELINE config 4 at full width (K=125, B=999) and a long horizon the oracle cannot reach in seconds:
+    size-independent properties -- used budget equals the selected row, optimum is monotone in the radius,
+    B'=0 returns u_old, and the objective re-evaluated along the returned trajectory equals the table value."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.synthetic(n=6000, B=999, seed=20251018)
+    plan = gpu_lib.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt)
+    plan.bellman(inst.df, inst.u_old)
+    assert plan.count_updates() == oracle.count_updates(inst.u_old, inst.B, inst.nu, inst.iterator)
+    d = dict(nu=inst.nu, it=inst.iterator, dt=inst.dt, df=inst.df)
+    prev = None
+    for Bn in (999, 499, 249, 124, 10, 0):
+        u = np.zeros_like(inst.u_old)
+        ps, bs, ks = plan.eval_u(u, Bn)
+        used = int(np.abs(u - inst.u_old).sum())
+        assert used == bs <= Bn
+        if prev is not None:
+            assert ps >= prev
+        prev = ps
+        if Bn == 0:
+            np.testing.assert_array_equal(u, inst.u_old)
+        obj = objective_of(oracle, u, d, plan.cost)
+        assert abs(obj - ps) <= 1e-9 * max(1.0, abs(obj))
+    # the two kernel paths agree bit for bit at this size as well
+    plan2 = gpu_lib.TRMPlan(inst.nu, inst.iterator, 600, inst.B, inst.beta, inst.p, inst.dt, flags=1)
+    plan3 = gpu_lib.TRMPlan(inst.nu, inst.iterator, 600, inst.B, inst.beta, inst.p, inst.dt)
+    plan2.bellman(inst.df[:600], inst.u_old[:600]); plan3.bellman(inst.df[:600], inst.u_old[:600])
+    np.testing.assert_array_equal(plan2.export_phi(), plan3.export_phi())
+    u2, u3 = np.zeros((600, 3)), np.zeros((600, 3))
+    assert plan2.eval_u(u2, 700) == plan3.eval_u(u3, 700)
+    np.testing.assert_array_equal(u2, u3)
+    for p_ in (plan, plan2, plan3):
+        p_.close()
