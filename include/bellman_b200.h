@@ -172,6 +172,13 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count);
  * counted as 2 FP64 ops).  Runs a full-chip kernel for about target_ms; returns lane-operations per second. */
 int bb200_fp64_peak(int device, int32_t mode, double target_ms, double *ops_per_s, double *elapsed_ms);
 
+/* In-kernel cycle profile of the wavefront kernel.  enable != 0 switches the counters on for later launches;
+ * if out != NULL the counters of the last launch are copied out, 16 int64 per CTA for min(max_ctas, SMs) CTAs:
+ *   [0..4]  compute warp 0: cycles waiting for rows, in phase B, at the CTA barrier, in phase C; stages
+ *   [8..13] comm warp: cycles in stage-cost evaluation, neighbour waits, halo gather, waiting for compute,
+ *           publishing progress; stages */
+int bb200_profile(bb200_plan *plan, int32_t enable, int64_t *out, int32_t max_ctas);
+
 /* Tuning knobs for experiments (0 = automatic): number of CTAs, j-split, rows per thread. */
 int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t variant);
 

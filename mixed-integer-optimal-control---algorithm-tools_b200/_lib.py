@@ -48,6 +48,7 @@ SIGNATURES = {
     "bb200_pred_integral": (ctypes.c_int, [c_plan_p, ctypes.c_int32, _F64P]),
     "bb200_tv": (ctypes.c_int, [c_plan_p, ctypes.c_int32, ctypes.c_double, _F64P]),
     "bb200_stats": (ctypes.c_int, [c_plan_p, _F64P, ctypes.c_int32]),
+    "bb200_profile": (ctypes.c_int, [c_plan_p, ctypes.c_int32, _I64P, ctypes.c_int32]),
     "bb200_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, ctypes.c_double, _F64P, _F64P]),
 }
 

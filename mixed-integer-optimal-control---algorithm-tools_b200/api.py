@@ -164,6 +164,12 @@ class TRMPlan:
                 "device_bytes", "threads", "jsplit", "wave_ms")
         return dict(zip(keys, out.tolist()))
 
+    def profile(self, enable=True, fetch=False, max_ctas=148):
+        """Switch the wavefront kernel's cycle counters on/off; fetch=True returns the last launch's (ctas, 16) array."""
+        out = np.zeros((max_ctas, 16), dtype=np.int64) if fetch else None
+        _lib.check(self.lib.bb200_profile(self._h, int(enable), _lib.i64p(out), max_ctas if fetch else 0))
+        return out
+
     def close(self):
         self._fin()
 

@@ -45,7 +45,8 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 struct SlotHost {
-    double *df = nullptr, *u_old = nullptr, *u = nullptr, *phi = nullptr, *rec = nullptr;
+    double *df = nullptr, *u_old = nullptr, *u = nullptr, *phi = nullptr, *rec = nullptr, *ss_all = nullptr;
+    int *bt_all = nullptr;
     void *arg = nullptr;
     unsigned long long *n_updates = nullptr;
     bool has_dp = false;
@@ -70,6 +71,8 @@ struct bb200_plan {
     long long *d_goff = nullptr;
     unsigned long long *d_flags = nullptr;
     int *d_err = nullptr, *d_btmax = nullptr;
+    long long *d_prof = nullptr;
+    bool prof_on = false;
     SlotDev *d_slots = nullptr;
     std::vector<SlotHost> slots;
     std::vector<SlotDev> slots_dev;
@@ -126,11 +129,12 @@ void destroy_plan(bb200_plan *p)
     if (p->own_stream) cudaStreamSynchronize(p->own_stream);
     for (auto &s : p->slots) {
         cudaFree(s.df); cudaFree(s.u_old); cudaFree(s.u); cudaFree(s.phi); cudaFree(s.rec);
-        cudaFree(s.arg); cudaFree(s.n_updates);
+        cudaFree(s.arg); cudaFree(s.n_updates); cudaFree(s.ss_all); cudaFree(s.bt_all);
     }
     cudaFree(p->d_lvd); cudaFree(p->d_cost); cudaFree(p->d_halo); cudaFree(p->d_scalar);
     cudaFree(p->d_goff); cudaFree(p->d_flags); cudaFree(p->d_err); cudaFree(p->d_btmax);
     cudaFree(p->d_slots);
+    cudaFree(p->d_prof);
     if (p->h_rec) cudaFreeHost(p->h_rec);
     if (p->h_err) cudaFreeHost(p->h_err);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
@@ -160,6 +164,7 @@ int queue_dp(bb200_plan *p, int slot0, int count)
         c.flags = p->d_flags;
         c.err = p->d_err;
         c.btmax = p->d_btmax;
+        c.prof = p->prof_on ? p->d_prof : nullptr;
         CU(cudaEventRecord(p->ev[4], st));
         CU(launch_wavefront(p->tab, c, p->argw, st));
         CU(cudaEventRecord(p->ev[5], st));
@@ -271,7 +276,7 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
 
     bb200_plan *p = new bb200_plan();
     p->device = device; p->n = n; p->M = M; p->K = K; p->B = B; p->B1 = (int)(B + 1);
-    p->Kp = (K + 15) / 16 * 16; p->dt = dt; p->batch = batch; p->flags = flags; p->G = G;
+    p->Kp = (K + 31) / 32 * 32; p->dt = dt; p->batch = batch; p->flags = flags; p->G = G;
     p->argw = (K <= 255) ? 1 : 2;
     p->nPad = (n + kChunk - 1) / kChunk * kChunk;
     p->grid_dims.assign(grid_dims, grid_dims + M);
@@ -300,6 +305,7 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
     if ((rc = dev_alloc(p, &p->d_flags, (size_t)prop.multiProcessorCount * kFlagStride))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_halo, (size_t)kHaloRing * p->B1 * p->Kp))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_slots, (size_t)batch))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_prof, (size_t)prop.multiProcessorCount * 16))) return bail(rc);
 #define CUB(call)                                                                                   \
     do {                                                                                            \
         cudaError_t e_ = (call);                                                                    \
@@ -326,6 +332,8 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
         if ((rc = dev_alloc(p, &h.phi, (size_t)2 * p->B1 * p->Kp))) return bail(rc);
         if ((rc = dev_alloc(p, &h.rec, (size_t)4 * kMaxRadii))) return bail(rc);
         if ((rc = dev_alloc(p, &h.n_updates, 1))) return bail(rc);
+        if ((rc = dev_alloc(p, &h.ss_all, (size_t)n * p->Kp))) return bail(rc);
+        if ((rc = dev_alloc(p, &h.bt_all, (size_t)n * p->Kp))) return bail(rc);
         unsigned char *a = nullptr;
         if ((rc = dev_alloc(p, &a, argcells * p->argw))) return bail(rc);
         h.arg = a;
@@ -334,7 +342,7 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
         CUB(cudaMemset(h.u, 0, io * sizeof(double)));
         SlotDev &d = p->slots_dev[s];
         d.df = h.df; d.u_old = h.u_old; d.u = h.u; d.phi = h.phi; d.arg = h.arg;
-        d.n_updates = h.n_updates; d.rec = h.rec;
+        d.n_updates = h.n_updates; d.rec = h.rec; d.ss_all = h.ss_all; d.bt_all = h.bt_all;
     }
     CUB(cudaMemcpy(p->d_slots, p->slots_dev.data(), sizeof(SlotDev) * batch, cudaMemcpyHostToDevice));
     CUB(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
@@ -646,6 +654,19 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv)
     CU(cudaMemcpyAsync(plan->h_rec, plan->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
     CU(cudaStreamSynchronize(plan->stream));
     *tv = plan->h_rec[0];
+    return BB200_OK;
+}
+
+int bb200_profile(bb200_plan *plan, int32_t enable, int64_t *out, int32_t max_ctas)
+{
+    if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
+    Guard g(plan);
+    plan->prof_on = enable != 0;
+    if (out && max_ctas > 0) {
+        CU(cudaStreamSynchronize(plan->stream));
+        const int nct = std::min<int>(max_ctas, plan->num_sms);
+        CU(cudaMemcpy(out, plan->d_prof, (size_t)nct * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
     return BB200_OK;
 }
 

@@ -2,10 +2,12 @@
 //
 // Device data layout (all per plan unless "per slot"):
 //   lvd   double[K][M]    level values nu_k[m] as Float64 (HelpFunctions.jl:54-56 converts Int64->Float64)
+//   Kp = K rounded up to a multiple of 32 (one warp-wide row segment)
 //   cost  double[K][Kp]   cost[j*Kp + l] jump cost successor j (stage i+1) <- level l (stage i); pad = +Inf
 //   goff  int64[K]        column-major grid offset of admissible tuple k
 //   per slot:
 //   df, u_old, u  double[nPad][M]   reference layout (Julia M x n), rows padded to the TMA chunk
+//   ss_all double[n][Kp], bt_all int[n][Kp]  per-stage level costs / budget uses (S3), written once per DP by prep
 //   phi   double[2][B1][Kp]  exit state (S7): [0] = stage-1 values, [1] = stage-2 values, level fastest
 //   arg   ArgT[n-1][B1][Kp]  packed argmin, indexed by SOURCE budget row b' = b - b~_l(i):
 //                            arg[i-1][b'][l] = winner j of target cell (b' + b~_l(i), l) at stage i
@@ -17,7 +19,8 @@
 namespace bb200 {
 
 constexpr int kChunk = 64;        // stages per TMA chunk of df / u_old
-constexpr int kMaxWaveThreads = 256;  // wavefront CTA size cap: keeps 255 registers per thread available
+constexpr int kWaveThreadsBig = 256;    // wavefront CTA cap for large register tiles (7 compute warps + comm): 255 regs/thread
+constexpr int kWaveThreadsSmall = 512;  // cap for small tiles (15 compute warps + comm): 128 regs/thread
 constexpr int kMaxM = 8;          // controls supported by the kernels
 constexpr int kFlagStride = 16;   // u64 words between per-CTA progress flags (128 B apart)
 constexpr int kHaloRing = 8;      // stages of halo kept in flight between neighbouring CTAs
@@ -28,6 +31,8 @@ struct SlotDev {
     double *u;            // [nPad][M]
     double *phi;          // [2][B1][Kp]
     void *arg;            // ArgT[n-1][B1][Kp]
+    double *ss_all;       // [n][Kp] stage cost s_l(i) of stage i in row i-1 (filled by the prep kernel)
+    int *bt_all;          // [n][Kp] budget use b~_l(i), clamped to B1 = unreachable; pad levels hold B1
     unsigned long long *n_updates;  // exact relaxation count of the last DP
     double *rec;          // [4] phi_star, b_star, k_star, status of the last selection
 };

@@ -11,13 +11,21 @@
 //     g-1 .. g-D only (D = ceil(max b~ / R)): the slices form a pipeline and low-budget CTAs run ahead in
 //     time.  Neighbours synchronise through per-CTA progress counters in global memory (release/acquire),
 //     never through a grid-wide barrier.
-//   * Inside a CTA the stage is a small min-plus matrix product C[b', l] = min_j (s_l + c_jl) + P[b', j].
-//     A thread owns a TB x TL register tile of cells (TB source rows, TL levels), thread groups split the
-//     successor range j (JS groups); every candidate is two separately rounded FP64 adds and a strict '>'
-//     (earliest successor wins ties, +Inf/NaN never win) -- exactly the reference's arithmetic.  Partial
-//     (min, argmin) pairs of the JS groups are combined in ascending-j order through shared memory.
-//   * df[:, i] and u_old[:, i] arrive in kChunk-stage chunks by 1-D bulk TMA (cp.async.bulk + mbarrier).
-//   * The argmin goes to HBM once per cell as uint8/uint16, indexed by source row (coalesced rows).
+//   * Warp specialisation inside a CTA.  COMPUTE warps do the arithmetic; one COMM warp runs one stage
+//     ahead: it brings the stage's level costs s_l(i) and budget uses b~_l(i) (evaluated from df[:, i] and
+//     u_old[:, i] by the prep kernel, S3) and the halo rows the predecessors pushed into shared memory by 1-D
+//     bulk TMA (cp.async.bulk + mbarrier), polls the neighbours' progress counters, merges the halo cells
+//     (and the +Inf of unreachable cells) into the next value rows, and publishes this CTA's own progress.  Compute and comm hand over through two shared-memory mbarriers
+//     (`full`: rows ready, `done`: stage finished), so no global-memory latency is exposed in steady state.
+//   * Phase B (compute): the stage is a small min-plus matrix product C[b', l] = min_j (s_l + c_jl) + P[b', j].
+//     A thread owns a TB x TL register tile of cells, thread groups split the successor range j (JS groups).
+//     Every candidate is two separately rounded FP64 adds (:67, :71) and a strict '>' (:73) that keeps the
+//     earliest successor on ties and never lets +Inf/NaN win -- exactly the reference's arithmetic.  On sm_100a
+//     an FP64 instruction occupies two issue slots, so a candidate costs DADD(2)+DSETP(2)+2 FSEL+SEL = 7 slots
+//     (profiles/pipe_probe_r01.txt); the kernel is issue bound, not FP64-pipe or HBM bound.
+//   * Phase C (compute): the JS partial (min, argmin) pairs of a cell are combined in ascending-j order with the
+//     same strict '>' (the earliest group holding the minimum wins).  The value goes to the next stage's rows (own slice: shared memory; higher slice: global halo ring), the
+//     argmin to HBM once per cell as uint8/uint16 indexed by source row (coalesced rows).
 #include "bb200_internal.cuh"
 #include "kernels.cuh"
 
@@ -37,6 +45,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -72,6 +84,21 @@ __device__ __forceinline__ void st_release(unsigned long long *p, unsigned long 
 {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void compute_barrier(int nthreads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
 // Spin until *flag >= want.  A bounded watchdog turns a lost dependency into an error code instead of a
 // hung GPU: after ~2^24 polls the CTA raises the abort flag and every poller gives up.
@@ -79,7 +106,7 @@ __device__ __forceinline__ void wait_flag(const unsigned long long *flag, long l
 {
     if (want <= 0) return;
     unsigned int spins = 0;
-    while ((long long)ld_acquire(flag) < want) {
+    while ((long long)ld_relaxed(flag) < want) {  // relaxed polls; the caller fences once after all waits
         if ((++spins & 0x3ffu) == 0) {
             if (*(volatile int *)&err[3]) return;
             if (spins > (1u << 24)) {
@@ -92,305 +119,391 @@ __device__ __forceinline__ void wait_flag(const unsigned long long *flag, long l
 }
 
 struct Smem {
-    uint64_t *mbar;   // [2]
-    double *dfb;      // [2][kChunk*M]
-    double *uob;      // [2][kChunk*M]
-    double *lvs;      // [K*M]
-    double *ss;       // [Kp]
-    int *bts;         // [2][Kp]
-    double *Ps;       // [2][Kp*RP]
-    double *cs;       // [K*Kp]
-    double *pv;       // [JS*R*Kp]
-    unsigned char *pa;  // ArgT[JS*R*Kp]
+    uint64_t *mbar;   // [0..1] cost rows landed (per parity), [2] halo landed, [3] full, [4] done
+    double *ss;       // [2][Kp]   stage cost of stage i in ss[i&1]         (TMA destination)
+    int *bts;         // [2][Kp]   budget use of stage i in bts[i&1]        (TMA destination)
+    double *hst;      // [R][Kp]   halo rows pushed by lower slices         (TMA destination)
+    double *Ps;       // [2][Kp*RP] value rows read by stage i in Ps[i&1]
+    double *cs;       // [K*Kp]    jump costs
+    double *pv;       // [JS*R*Kp] partial minima of the j-groups
+    unsigned char *pa;  // ArgT[JS*R*Kp] partial argmins
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Carves the dynamic shared memory; argw = bytes per partial argmin entry (1 or 2).
-__host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int argw, unsigned char *base,
-                                        Smem *s)
+__host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int argw, unsigned char *base, Smem *s)
 {
     size_t off = 0;
-    size_t o[10];
-    const size_t chunk = (size_t)kChunk * t.M * sizeof(double);
-    const size_t sizes[10] = {2 * sizeof(uint64_t),
-                              2 * chunk,
-                              2 * chunk,
-                              (size_t)t.K * t.M * sizeof(double),
-                              (size_t)t.Kp * sizeof(double),
-                              2 * (size_t)t.Kp * sizeof(int),
-                              2 * (size_t)t.Kp * c.RP * sizeof(double),
-                              (size_t)t.K * t.Kp * sizeof(double),
-                              (size_t)c.JS * c.R * t.Kp * sizeof(double),
-                              (size_t)c.JS * c.R * t.Kp * (size_t)argw};
-    for (int k = 0; k < 10; ++k) {
+    size_t o[8];
+    const size_t sizes[8] = {8 * sizeof(uint64_t),
+                             2 * (size_t)t.Kp * sizeof(double),
+                             2 * (size_t)t.Kp * sizeof(int),
+                             (size_t)c.R * t.Kp * sizeof(double),
+                             2 * (size_t)t.Kp * c.RP * sizeof(double),
+                             (size_t)t.K * t.Kp * sizeof(double),
+                             (size_t)c.JS * c.R * t.Kp * sizeof(double),
+                             (size_t)c.JS * c.R * t.Kp * (size_t)argw};
+    for (int k = 0; k < 8; ++k) {
         o[k] = off;
         off = align_up(off + sizes[k], 128);
     }
     if (s) {
         s->mbar = reinterpret_cast<uint64_t *>(base + o[0]);
-        s->dfb = reinterpret_cast<double *>(base + o[1]);
-        s->uob = reinterpret_cast<double *>(base + o[2]);
-        s->lvs = reinterpret_cast<double *>(base + o[3]);
-        s->ss = reinterpret_cast<double *>(base + o[4]);
-        s->bts = reinterpret_cast<int *>(base + o[5]);
-        s->Ps = reinterpret_cast<double *>(base + o[6]);
-        s->cs = reinterpret_cast<double *>(base + o[7]);
-        s->pv = reinterpret_cast<double *>(base + o[8]);
-        s->pa = base + o[9];
+        s->ss = reinterpret_cast<double *>(base + o[1]);
+        s->bts = reinterpret_cast<int *>(base + o[2]);
+        s->hst = reinterpret_cast<double *>(base + o[3]);
+        s->Ps = reinterpret_cast<double *>(base + o[4]);
+        s->cs = reinterpret_cast<double *>(base + o[5]);
+        s->pv = reinterpret_cast<double *>(base + o[6]);
+        s->pa = base + o[7];
     }
     return off;
 }
 
+// Phase B of one thread: TB x TL cells, successors [jb, je): the reference's innermost loop (HelpFunctions.jl:71-76).
+//   Prow: value rows of this thread's row group, [j][RP];  crow: jump costs of its levels, [j][Kp]
+//   srow: stage costs of its levels;  pv/pa: partial (min, argmin) out, [r][Kp]
+// Cost per candidate and cell on sm_100a: DADD + DSETP (two issue slots each) + 2 FSEL + SEL = 7 slots.
 template <int TB, int TL, typename ArgT>
-__global__ void __launch_bounds__(kMaxWaveThreads, 1) wavefront_kernel(Tables t, WaveCfg c)
+__device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const double *__restrict__ crow,
+                                        const double *__restrict__ srow, double *__restrict__ pv,
+                                        ArgT *__restrict__ pa, int jb, int je, int RP, int Kp)
+{
+    constexpr int TBP = (TB + 1) & ~1;
+    constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
+    const double inf = d_inf();
+    double best[TB][TL];
+    int arg[TB][TL];
+#pragma unroll
+    for (int a = 0; a < TB; ++a)
+#pragma unroll
+        for (int q = 0; q < TL; ++q) { best[a][q] = inf; arg[a][q] = MARKI; }
+    double s[TL];
+#pragma unroll
+    for (int q = 0; q < TL; ++q) s[q] = srow[q];
+#pragma unroll 2
+    for (int j = jb; j < je; ++j) {
+        double p[TBP];
+#pragma unroll
+        for (int k = 0; k < TBP / 2; ++k) {
+            const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)j * RP + 2 * k);
+            p[2 * k] = x.x;
+            p[2 * k + 1] = x.y;
+        }
+        double a[TL];
+        if constexpr (TL % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < TL / 2; ++k) {
+                const double2 x = *reinterpret_cast<const double2 *>(crow + (size_t)j * Kp + 2 * k);
+                a[2 * k] = __dadd_rn(s[2 * k], x.x);  // HelpFunctions.jl:67
+                a[2 * k + 1] = __dadd_rn(s[2 * k + 1], x.y);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < TL; ++q) a[q] = __dadd_rn(s[q], crow[(size_t)j * Kp + q]);
+        }
+#pragma unroll
+        for (int q = 0; q < TL; ++q) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r) {
+                const double v = __dadd_rn(a[q], p[r]);               // :71
+                if (best[r][q] > v) { best[r][q] = v; arg[r][q] = j; }  // :73-76, strict: the earliest j wins
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TB; ++r)
+#pragma unroll
+        for (int q = 0; q < TL; ++q) {
+            pv[(size_t)r * Kp + q] = best[r][q];
+            pa[(size_t)r * Kp + q] = (ArgT)arg[r][q];
+        }
+}
+
+// ======================================= COMM warp ===============================================
+template <int TB>
+__device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane)
+{
+    constexpr int TBP = (TB + 1) & ~1;
+    const int g = blockIdx.x;
+    const int r0 = g * c.R;
+    const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, RP = c.RP, n = t.n;
+    const double inf = d_inf();
+    uint64_t *mb_cost = &sm.mbar[0], *mb_halo = &sm.mbar[2], *mb_full = &sm.mbar[3], *mb_done = &sm.mbar[4];
+    const int btm = min(*c.btmax, B1 - 1);
+    const int D = (btm + R - 1) / R;  // slices a push can span
+    const int my_rows = min(R, B1 - r0);  // rows of this slice that exist in the table (>= 1)
+    const int lblocks = Kp >> 5;
+    unsigned long long *myflag = c.flags + (size_t)g * kFlagStride;
+    uint32_t cost_phase = 0;  // parity bit per cost buffer
+    uint32_t halo_phase = 0, done_phase = 0;
+    long long tick0 = 0;  // tick of the terminal stage of the current subproblem; stage i has tick0 + n - i
+    long long pc[6] = {0, 0, 0, 0, 0, 0};  // profile: cost wait, flag wait, halo TMA + merge, done wait, publish, stages
+    long long tp = clock64();
+#define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
+    auto rowpos = [&](int row) { return (row / TB) * TBP + (row % TB); };
+    // level costs / budget uses of stage i (row i-1 of the prep kernel's tables) into buffer i&1
+    auto load_costs = [&](const SlotDev &sl, int i) {
+        const int b = i & 1;
+        mbar_expect_tx(&mb_cost[b], (uint32_t)(Kp * (sizeof(double) + sizeof(int))));
+        tma_load_1d(sm.ss + (size_t)b * Kp, sl.ss_all + (size_t)(i - 1) * Kp, (uint32_t)(Kp * sizeof(double)), &mb_cost[b]);
+        tma_load_1d(sm.bts + (size_t)b * Kp, sl.bt_all + (size_t)(i - 1) * Kp, (uint32_t)(Kp * sizeof(int)), &mb_cost[b]);
+    };
+    auto wait_costs = [&](int i) {
+        mbar_wait(&mb_cost[i & 1], (cost_phase >> (i & 1)) & 1u);
+        cost_phase ^= 1u << (i & 1);
+    };
+
+    for (int sub = 0; sub < c.nsub; ++sub, tick0 += n) {
+        const SlotDev sl = c.slots[sub];
+        if (lane == 0) {
+            load_costs(sl, n);                  // terminal stage
+            if (n >= 2) load_costs(sl, n - 1);  // first computed stage
+        }
+        wait_costs(n);
+        if (n == 1) {
+            // only the terminal stage exists: it is the exit state (slot 1 of the reference)
+            for (int x = lane; x < my_rows * Kp; x += 32) {
+                const int row = x / Kp, l = x % Kp;
+                if (l < K) sl.phi[(size_t)(r0 + row) * Kp + l] = (r0 + row == sm.bts[Kp + l]) ? sm.ss[Kp + l] : inf;
+            }
+            __syncwarp();
+            continue;
+        }
+
+        for (int s = n - 1; s >= 0; --s) {
+            const long long tick_s = tick0 + (n - s);  // tick of stage s
+            if (s >= 1) {
+                double *Pw = sm.Ps + (size_t)(s & 1) * Kp * RP;
+                if (s == n - 1) {
+                    // ---- terminal stage n (HelpFunctions.jl:27-43) = the rows stage n-1 reads ----------------
+                    // P[b][l] = (b == b~_l(n)) ? s_l(n) : Inf
+                    const double *sn = sm.ss + (size_t)(n & 1) * Kp;
+                    const int *bn = sm.bts + (size_t)(n & 1) * Kp;
+                    for (int row = 0; row < my_rows; ++row)
+                        for (int blk = 0; blk < lblocks; ++blk) {
+                            const int l = (blk << 5) + lane, b = r0 + row;
+                            if (l < K) {
+                                const double v = (b == bn[l]) ? sn[l] : inf;
+                                Pw[l * RP + rowpos(row)] = v;
+                                if (n == 2) sl.phi[((size_t)B1 + b) * Kp + l] = v;  // stage 2 is exit slot 2
+                            }
+                        }
+                    __syncwarp();
+                    // the terminal costs are consumed: their buffer takes the costs of stage n-2
+                    if (lane == 0 && n - 2 >= 1) load_costs(sl, n - 2);
+                }
+                wait_costs(s);
+                PROF_LAP(0);
+                // ---- neighbour waits, one progress counter per lane --------------------------------------
+                //   data (s <= n-2): predecessors finished stage s+1 (tick_s - 1): their pushes are visible
+                //   back-pressure: successors consumed the ring slot stage s will overwrite
+                for (int idx = lane; idx < 2 * D; idx += 32) {
+                    if (idx < D) {
+                        const int d = idx + 1;
+                        if (s <= n - 2 && d <= g)
+                            wait_flag(c.flags + (size_t)(g - d) * kFlagStride, tick_s - 1, c.err);
+                    } else {
+                        const int d = idx - D + 1;
+                        if (g + d < c.G)
+                            wait_flag(c.flags + (size_t)(g + d) * kFlagStride, tick_s - kHaloRing + 1, c.err);
+                    }
+                }
+                fence_gpu();  // acquire side of the relaxed polls
+                __syncwarp();
+                PROF_LAP(1);
+                if (s <= n - 2) {
+                    // ---- halo rows of my slice, pushed by lower slices during stage s+1: one bulk TMA ----------
+                    if (g > 0 && D > 0) {
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy read
+                            const uint32_t bytes = (uint32_t)((size_t)my_rows * Kp * sizeof(double));
+                            mbar_expect_tx(mb_halo, bytes);
+                            tma_load_1d(sm.hst, c.halo + ((size_t)((tick_s - 1) % kHaloRing) * B1 + r0) * Kp, bytes, mb_halo);
+                        }
+                        mbar_wait(mb_halo, halo_phase);
+                        halo_phase ^= 1u;
+                    }
+                    // ---- merge: cells of my rows produced by a lower slice (halo) or by nobody (+Inf) ---------
+                    const int *bt_prev = sm.bts + (size_t)((s + 1) & 1) * Kp;
+                    for (int row = 0; row < my_rows; ++row) {
+                        const int b = r0 + row, rp = rowpos(row);
+#pragma unroll 4
+                        for (int blk = 0; blk < lblocks; ++blk) {
+                            const int l = (blk << 5) + lane;
+                            const int src = b - bt_prev[l];
+                            if (l < K && src < r0) Pw[l * RP + rp] = (src >= 0) ? sm.hst[row * Kp + l] : inf;
+                        }
+                    }
+                }
+                PROF_LAP(2);
+            }
+            // ---- hand-over: wait for the compute warps to finish stage s+1, then release stage s -----------
+            const bool have_done = (s + 1 <= n - 1);
+            if (have_done) {
+                mbar_wait(mb_done, done_phase);
+                done_phase ^= 1u;
+            }
+            if (s >= 1) mbar_arrive(mb_full);
+            PROF_LAP(3);
+            if (have_done) {
+                // the pushes of stage s+1 (made by the compute threads, observed through `done`) become
+                // visible GPU-wide before the progress counter moves
+                if (lane == 0) {
+                    fence_gpu();
+                    st_relaxed(myflag, (unsigned long long)(tick_s - 1));
+                    // stage s+1 is finished, so its cost buffer is free: fetch the costs of stage s-1 into it
+                    if (s - 1 >= 1) load_costs(sl, s - 1);
+                }
+            }
+            PROF_LAP(4);
+            pc[5] += 1;
+        }
+    }
+    if (c.prof && lane == 0)
+        for (int k = 0; k < 6; ++k) c.prof[(size_t)g * 16 + 8 + k] = pc[k];
+#undef PROF_LAP
+}
+
+// MAXT is a multiple of 128: the register file is split evenly over the four schedulers, so the per-thread
+// budget is set by the scheduler that hosts the most warps.
+template <int TB, int TL, typename ArgT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 {
     constexpr int TBP = (TB + 1) & ~1;  // row positions per row group (even: 16-byte aligned loads)
     constexpr ArgT MARK = (ArgT)~(ArgT)0;
-    constexpr int MARKI = (int)MARK;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem sm;
     carve(t, c, (int)sizeof(ArgT), smem_raw, &sm);
 
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x;
+    const int NC = c.JS * c.tpg;  // compute threads; the comm warp is threads [NC, NC+32)
     const int g = blockIdx.x;
     const int r0 = g * c.R;
-    const int K = t.K, Kp = t.Kp, M = t.M, B1 = t.B1, R = c.R, RP = c.RP;
+    const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, RP = c.RP, n = t.n;
+    const double inf = d_inf();
+    uint64_t *mb_full = &sm.mbar[3], *mb_done = &sm.mbar[4];
+
+    // one-time: jump costs into shared memory, value rows and halo staging to +Inf, barriers
+    for (int x = tid; x < K * Kp; x += blockDim.x) sm.cs[x] = t.cost[x];
+    for (int x = tid; x < 2 * Kp * RP; x += blockDim.x) sm.Ps[x] = inf;
+    for (int x = tid; x < R * Kp; x += blockDim.x) sm.hst[x] = inf;
+    if (tid == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        mbar_init(&sm.mbar[2], 1);
+        mbar_init(mb_full, 32);
+        mbar_init(mb_done, NC);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= NC) {
+        comm_warp<TB>(t, c, sm, tid - NC);
+        return;
+    }
+
+    // ========================================= COMPUTE warps ============================================
+    auto rowpos = [&](int row) { return (row / TB) * TBP + (row % TB); };
     const int jg = tid / c.tpg, tig = tid % c.tpg;
     const bool active = tig < c.RG * c.nLG;
     const int rg = active ? tig / c.nLG : 0;
     const int lg = active ? tig % c.nLG : 0;
     const int jb = jg * c.jper;
     const int je = min(K, jb + c.jper);
-    const double inf = d_inf();
-    const uint32_t chunk_bytes = (uint32_t)(kChunk * M * sizeof(double));
+    uint32_t full_phase = 0;
+    long long tick0 = 0;
+    long long pc[5] = {0, 0, 0, 0, 0};  // profile: full wait, phase B, barrier, phase C, stages
+    long long tp = clock64();
+#define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
 
-    // one-time: constant tables into shared memory
-    for (int x = tid; x < K * Kp; x += NT) sm.cs[x] = t.cost[x];
-    for (int x = tid; x < K * M; x += NT) sm.lvs[x] = t.lvd[x];
-    if (tid == 0) {
-        mbar_init(&sm.mbar[0], 1);
-        mbar_init(&sm.mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int btm = min(*c.btmax, B1 - 1);
-    const int D = (btm + R - 1) / R;  // predecessor / successor slices a push can span
-    unsigned long long *myflag = c.flags + (size_t)g * kFlagStride;
-    uint32_t phase_bits = 0;  // mbarrier parity per chunk buffer
-    long long tick = 0;       // stages completed by this CTA in this launch (monotone across subproblems)
-
-    auto rowpos = [&](int row) { return (row / TB) * TBP + (row % TB); };
-
-    for (int sub = 0; sub < c.nsub; ++sub) {
+    for (int sub = 0; sub < c.nsub; ++sub, tick0 += n) {
         const SlotDev sl = c.slots[sub];
         ArgT *argtab = reinterpret_cast<ArgT *>(sl.arg);
-        const int n = t.n;
-        int chunk_cur = (n - 1) / kChunk;  // chunk holding the terminal stage row n-1
-        __syncthreads();                   // previous subproblem fully done with the chunk buffers
-        if (tid == 0) {
-            const int b0 = chunk_cur & 1;
-            mbar_expect_tx(&sm.mbar[b0], 2 * chunk_bytes);
-            tma_load_1d(sm.dfb + (size_t)b0 * kChunk * M, sl.df + (size_t)chunk_cur * kChunk * M, chunk_bytes,
-                        &sm.mbar[b0]);
-            tma_load_1d(sm.uob + (size_t)b0 * kChunk * M, sl.u_old + (size_t)chunk_cur * kChunk * M,
-                        chunk_bytes, &sm.mbar[b0]);
-            if (chunk_cur >= 1) {
-                const int b1 = (chunk_cur - 1) & 1;
-                mbar_expect_tx(&sm.mbar[b1], 2 * chunk_bytes);
-                tma_load_1d(sm.dfb + (size_t)b1 * kChunk * M, sl.df + (size_t)(chunk_cur - 1) * kChunk * M,
-                            chunk_bytes, &sm.mbar[b1]);
-                tma_load_1d(sm.uob + (size_t)b1 * kChunk * M, sl.u_old + (size_t)(chunk_cur - 1) * kChunk * M,
-                            chunk_bytes, &sm.mbar[b1]);
-            }
-        }
-        mbar_wait(&sm.mbar[chunk_cur & 1], (phase_bits >> (chunk_cur & 1)) & 1u);
-        phase_bits ^= 1u << (chunk_cur & 1);
-
-        // ---- terminal stage n (HelpFunctions.jl:27-43): P[b][l] = (b == b~_l(n)) ? s_l(n) : Inf ----
-        int cur = 0;
-        {
-            const int ri = n - 1;
-            const double *dfr = sm.dfb + ((size_t)(chunk_cur & 1) * kChunk + (ri % kChunk)) * M;
-            const double *uor = sm.uob + ((size_t)(chunk_cur & 1) * kChunk + (ri % kChunk)) * M;
-            for (int l = tid; l < Kp; l += NT) {
-                double s = 0.;
-                int bt = B1;
-                if (l < K) stage_cost(t, sm.lvs + l * M, dfr, uor, s, bt);
-                sm.ss[l] = s;
-                sm.bts[(tick & 1) * Kp + l] = bt;
-            }
-            __syncthreads();
-            double *Pc = sm.Ps + (size_t)cur * Kp * RP;
-            for (int x = tid; x < Kp * RP; x += NT) Pc[x] = inf;
-            __syncthreads();
-            for (int x = tid; x < R * Kp; x += NT) {
-                const int row = x / Kp, l = x % Kp;
-                const int b = r0 + row;
-                if (l < K && b < B1) {
-                    const bool hit = (b == sm.bts[(tick & 1) * Kp + l]);
-                    const double v = hit ? sm.ss[l] : inf;
-                    if (hit) Pc[l * RP + rowpos(row)] = v;
-                    if (n <= 2) sl.phi[((size_t)((n + 1) & 1) * B1 + b) * Kp + l] = v;
-                }
-            }
-            // (tick numbering: the terminal stage of subproblem `sub` is tick sub*n)
-            __syncthreads();
-            if (tid == 0) st_release(myflag, (unsigned long long)tick);
-        }
-
-        // ---- stages i = n-1 .. 1 --------------------------------------------------------------
         for (int i = n - 1; i >= 1; --i) {
-            ++tick;
-            const int ri = i - 1;
-            const int ch = ri / kChunk;
-            if (ch != chunk_cur) {
-                // first stage of a new chunk: everybody finished reading chunk ch+1 one barrier ago
-                chunk_cur = ch;
-                if (tid == 0 && ch >= 1) {
-                    const int b1 = (ch - 1) & 1;
-                    mbar_expect_tx(&sm.mbar[b1], 2 * chunk_bytes);
-                    tma_load_1d(sm.dfb + (size_t)b1 * kChunk * M, sl.df + (size_t)(ch - 1) * kChunk * M,
-                                chunk_bytes, &sm.mbar[b1]);
-                    tma_load_1d(sm.uob + (size_t)b1 * kChunk * M, sl.u_old + (size_t)(ch - 1) * kChunk * M,
-                                chunk_bytes, &sm.mbar[b1]);
-                }
-                mbar_wait(&sm.mbar[ch & 1], (phase_bits >> (ch & 1)) & 1u);
-                phase_bits ^= 1u << (ch & 1);
-            }
-            const int nxt = cur ^ 1;
-            double *Pc = sm.Ps + (size_t)cur * Kp * RP;
-            double *Pn = sm.Ps + (size_t)nxt * Kp * RP;
-            int *bt_cur = sm.bts + (tick & 1) * Kp;
-            const int *bt_prev = sm.bts + ((tick - 1) & 1) * Kp;
-            const bool need_halo = (i < n - 1) && (g > 0);
+            const long long tick = tick0 + (n - i);
+            const double *Pc = sm.Ps + (size_t)(i & 1) * Kp * RP;
+            double *Pn = sm.Ps + (size_t)((i - 1) & 1) * Kp * RP;
+            const double *ssc = sm.ss + (size_t)(i & 1) * Kp;
+            const int *bt_cur = sm.bts + (size_t)(i & 1) * Kp;
 
-            // ---- phase A: stage costs, neighbour waits, halo gather, +Inf fill of the next rows -----
+            mbar_wait(mb_full, full_phase);  // rows, stage costs and back-pressure for stage i are ready
+            full_phase ^= 1u;
+            PROF_LAP(0);
+
+            // ---- phase B: register-tiled min-plus scan over this group's successors (values only) --------
+            if (active)
+                phase_b<TB, TL, ArgT>(Pc + rg * TBP, sm.cs + lg * TL, ssc + lg * TL,
+                                      sm.pv + ((size_t)jg * R + rg * TB) * Kp + lg * TL,
+                                      reinterpret_cast<ArgT *>(sm.pa) + ((size_t)jg * R + rg * TB) * Kp + lg * TL, jb, je,
+                                      RP, Kp);
+            PROF_LAP(1);
+            compute_barrier(NC);
+            PROF_LAP(2);
+
+            // ---- phase C: combine the j-groups in ascending order, scatter the value, store the argmin --------
+            // Work unit = 32 consecutive levels of one source row (a warp-wide, coalesced row segment); every warp
+            // handles up to CU units at once so that the dependent compare chains of different cells overlap.
             {
-                const double *dfr = sm.dfb + ((size_t)(ch & 1) * kChunk + (ri % kChunk)) * M;
-                const double *uor = sm.uob + ((size_t)(ch & 1) * kChunk + (ri % kChunk)) * M;
-                for (int l = tid; l < Kp; l += NT) {
-                    double s = 0.;
-                    int bt = B1;
-                    if (l < K) stage_cost(t, sm.lvs + l * M, dfr, uor, s, bt);
-                    sm.ss[l] = s;
-                    bt_cur[l] = bt;
-                }
-                if (tid == NT - 1) {
-                    // data: predecessors finished the previous tick (their pushes are visible)
-                    if (need_halo)
-                        for (int d = 1; d <= D && d <= g; ++d)
-                            wait_flag(c.flags + (size_t)(g - d) * kFlagStride, tick - 1, c.err);
-                    // back-pressure: successors consumed the ring slot this tick overwrites
-                    for (int d = 1; d <= D && g + d < c.G; ++d)
-                        wait_flag(c.flags + (size_t)(g + d) * kFlagStride, tick - kHaloRing + 1, c.err);
-                }
-                for (int x = tid; x < Kp * RP; x += NT) Pn[x] = inf;
-                __syncthreads();
-                if (need_halo) {
-                    const double *hsrc = c.halo + (size_t)((tick - 1) % kHaloRing) * B1 * Kp;
-                    for (int x = tid; x < R * Kp; x += NT) {
-                        const int row = x / Kp, l = x % Kp;
-                        const int b = r0 + row;
-                        if (l < K && b < B1) {
-                            const int src = b - bt_prev[l];
-                            if (src >= 0 && src < r0) Pc[l * RP + rowpos(row)] = __ldcg(hsrc + (size_t)b * Kp + l);
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-
-            // ---- phase B: register-tiled min-plus scan over this group's successors ---------------
-            if (active) {
-                double best[TB][TL];
-                int arg[TB][TL];
-#pragma unroll
-                for (int a = 0; a < TB; ++a)
-#pragma unroll
-                    for (int q = 0; q < TL; ++q) { best[a][q] = inf; arg[a][q] = MARKI; }
-                double s[TL];
-#pragma unroll
-                for (int q = 0; q < TL; ++q) s[q] = sm.ss[lg * TL + q];
-                const double *Prow = Pc + rg * TBP;
-                const double *crow = sm.cs + lg * TL;
-#pragma unroll 2
-                for (int j = jb; j < je; ++j) {
-                    double p[TBP];
-#pragma unroll
-                    for (int k = 0; k < TBP / 2; ++k) {
-                        const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)j * RP + 2 * k);
-                        p[2 * k] = x.x;
-                        p[2 * k + 1] = x.y;
-                    }
-                    double a[TL];
-                    if constexpr (TL % 2 == 0) {
-#pragma unroll
-                        for (int k = 0; k < TL / 2; ++k) {
-                            const double2 x = *reinterpret_cast<const double2 *>(crow + (size_t)j * Kp + 2 * k);
-                            a[2 * k] = __dadd_rn(s[2 * k], x.x);          // HelpFunctions.jl:67
-                            a[2 * k + 1] = __dadd_rn(s[2 * k + 1], x.y);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < TL; ++q) a[q] = __dadd_rn(s[q], crow[(size_t)j * Kp + q]);
-                    }
-#pragma unroll
-                    for (int r = 0; r < TB; ++r)
-#pragma unroll
-                        for (int q = 0; q < TL; ++q) {
-                            const double v = __dadd_rn(a[q], p[r]);       // :71
-                            if (best[r][q] > v) { best[r][q] = v; arg[r][q] = j; }  // :73-76
-                        }
-                }
-                // partial results of this j-group
-                double *pv = sm.pv + ((size_t)jg * R + rg * TB) * Kp + lg * TL;
-                ArgT *pa = reinterpret_cast<ArgT *>(sm.pa) + ((size_t)jg * R + rg * TB) * Kp + lg * TL;
-#pragma unroll
-                for (int r = 0; r < TB; ++r)
-#pragma unroll
-                    for (int q = 0; q < TL; ++q) {
-                        pv[(size_t)r * Kp + q] = best[r][q];
-                        pa[(size_t)r * Kp + q] = (ArgT)arg[r][q];
-                    }
-            }
-            __syncthreads();
-
-            // ---- phase C: combine the j-groups in ascending order, scatter values, store the argmin --
-            {
+                constexpr int CU = 4;
                 double *hdst = c.halo + (size_t)(tick % kHaloRing) * B1 * Kp;
-                for (int x = tid; x < R * Kp; x += NT) {
-                    const int row = x / Kp, l = x % Kp;
-                    const int bsrc = r0 + row;
-                    if (l >= K || bsrc >= B1) continue;
-                    const int tgt = bsrc + bt_cur[l];
-                    if (tgt >= B1) continue;  // outside `for b = 0:B-b~` (:69): the reference computes nothing
-                    double val = inf;
-                    ArgT a = MARK;
-                    const ArgT *pa_all = reinterpret_cast<const ArgT *>(sm.pa);
-                    for (int q = 0; q < c.JS; ++q) {
-                        const double v = sm.pv[((size_t)q * R + row) * Kp + l];
-                        if (val > v) { val = v; a = pa_all[((size_t)q * R + row) * Kp + l]; }
+                const ArgT *pa_all = reinterpret_cast<const ArgT *>(sm.pa);
+                const int lblocks = Kp >> 5;
+                const int units = R * lblocks;
+                const int warp = tid >> 5, lane = tid & 31, nwarps = NC >> 5;
+                for (int u0 = warp; u0 < units; u0 += nwarps * CU) {
+                    double val[CU];
+                    int row_[CU], l_[CU], tgt_[CU], arg_[CU];
+                    bool ok[CU];
+#pragma unroll
+                    for (int u = 0; u < CU; ++u) {
+                        const int unit = u0 + u * nwarps;
+                        const bool live = unit < units;
+                        const int row = live ? unit / lblocks : 0;
+                        const int l = live ? ((unit - row * lblocks) << 5) + lane : lane;
+                        const int bsrc = r0 + row;
+                        const int tgt = bsrc + bt_cur[l];
+                        // cells outside `for b = 0:B-b~` (:69) are not computed by the reference either
+                        ok[u] = live && l < K && bsrc < B1 && tgt < B1;
+                        row_[u] = row; l_[u] = l; tgt_[u] = tgt;
+                        val[u] = inf; arg_[u] = (int)MARK;
                     }
-                    argtab[((size_t)(i - 1) * B1 + bsrc) * Kp + l] = a;
-                    if (tgt < r0 + R) Pn[l * RP + rowpos(tgt - r0)] = val;
-                    else hdst[(size_t)tgt * Kp + l] = val;
-                    if (i <= 2) sl.phi[((size_t)((i + 1) & 1) * B1 + tgt) * Kp + l] = val;
+                    for (int q = 0; q < c.JS; ++q) {
+#pragma unroll
+                        for (int u = 0; u < CU; ++u) {
+                            const size_t x = ((size_t)q * R + row_[u]) * Kp + l_[u];
+                            const double v = sm.pv[x];
+                            if (val[u] > v) { val[u] = v; arg_[u] = (int)pa_all[x]; }  // strict: earliest group wins ties
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < CU; ++u) {
+                        if (!ok[u]) continue;
+                        const int bsrc = r0 + row_[u];
+                        argtab[((size_t)(i - 1) * B1 + bsrc) * Kp + l_[u]] = (ArgT)arg_[u];
+                        if (tgt_[u] < r0 + R) Pn[l_[u] * RP + rowpos(tgt_[u] - r0)] = val[u];
+                        else hdst[(size_t)tgt_[u] * Kp + l_[u]] = val[u];
+                        if (i <= 2) sl.phi[((size_t)((i + 1) & 1) * B1 + tgt_[u]) * Kp + l_[u]] = val[u];
+                    }
                 }
             }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) st_release(myflag, (unsigned long long)tick);
-            cur = nxt;
+            mbar_arrive(mb_done);
+            PROF_LAP(3);
+            pc[4] += 1;
         }
-        ++tick;  // the next subproblem's terminal stage
     }
+    if (c.prof && tid == 0)
+        for (int k = 0; k < 5; ++k) c.prof[(size_t)g * 16 + k] = pc[k];
+#undef PROF_LAP
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-struct Variant { int TB, TL; };
-static const Variant kVariants[] = {{7, 4}, {8, 4}, {4, 4}, {8, 2}, {8, 1}, {4, 1}};
+struct Variant { int TB, TL, maxt; };
+// Large register tiles run with 8 compute warps (224 registers per thread); small tiles with up to 16 compute
+// warps (120 registers per thread), which hides the FP64 compare->select latency with more warps in flight.
+static const Variant kVariants[] = {{7, 4, kWaveThreadsBig},   {8, 4, kWaveThreadsBig},   {4, 4, kWaveThreadsSmall},
+                                    {7, 2, kWaveThreadsSmall}, {8, 2, kWaveThreadsSmall}, {8, 1, kWaveThreadsSmall},
+                                    {4, 1, kWaveThreadsSmall}};
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, WaveCfg &c)
@@ -399,7 +512,6 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, WaveC
     c.TB = kVariants[v].TB;
     c.TL = kVariants[v].TL;
     const int TBP = (c.TB + 1) & ~1;
-    c.G = G;
     const int rows_per_cta = (t.B1 + G - 1) / G;
     c.RG = (rows_per_cta + c.TB - 1) / c.TB;
     c.R = c.RG * c.TB;
@@ -409,7 +521,7 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, WaveC
     c.jper = (t.K + JS - 1) / JS;
     c.tpg = ((c.RG * c.nLG + 31) / 32) * 32;
     c.RP = c.RG * TBP;
-    c.threads = c.JS * c.tpg;
+    c.threads = c.JS * c.tpg + 32;  // + the comm warp
     c.smem = carve(t, c, argw, nullptr, nullptr);
 }
 
@@ -417,46 +529,46 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     int want_variant, WaveCfg &cfg)
 {
     if (t.M > kMaxM || t.K > 4096) return false;
-    // candidate search: prefer many CTAs, full lanes, and enough rows per CTA to amortise a stage
     double best_score = -1.;
     bool found = false;
     for (int v = 0; v < kNumVariants; ++v) {
         if (want_variant > 0 && v != want_variant - 1) continue;
-        // level groups must cover Kp-aligned vector loads: TL*nLG <= Kp is guaranteed by Kp = roundup16(K)
         if (((t.K + kVariants[v].TL - 1) / kVariants[v].TL) * kVariants[v].TL > t.Kp) continue;
         for (int js = 1; js <= 16; ++js) {
             if (want_js > 0 && js != want_js) continue;
             if (js > t.K) break;
             int gmax = want_ctas > 0 ? want_ctas : num_sms;
             if (gmax > num_sms) gmax = num_sms;
-            // tiny stages do not pay for inter-CTA pipelining: at least ~2 row tiles of work per CTA
             WaveCfg c = cfg;
             fill_geometry(t, argw, gmax, js, v, c);
-            if (c.threads > kMaxWaveThreads || c.threads < 32) continue;
+            if (c.threads > kVariants[v].maxt || c.threads < 64) continue;
             if (c.smem > smem_max) continue;
-            // score: relaxations per issue slot.  lanes used x tile efficiency, minus combine overhead.
-            const double lanes = (double)(c.RG * c.nLG) / c.tpg;
-            const double rows_eff = (double)t.B1 / ((double)c.G * c.R);
-            const double lev_eff = (double)t.K / (c.nLG * c.TL);
+            // Cost model per stage and CTA in scheduler cycles, fitted to the in-kernel profile on B200
+            // (profiles/phase_profile_r01.txt).  Phase B is issue bound: an FP64 instruction takes two issue slots,
+            // so a candidate costs DADD(2)+DSETP(2)+2 FSEL+SEL = 7 slots, plus the per-successor loads and the
+            // s_l + c_jl adds; the busiest scheduler hosts ceil(warps/4) warps; ~25% of the slots are lost to
+            // dependency stalls.  Phase C (combine + scatter) is latency bound and grows with the j-split.
+            const double warps = (double)(c.threads - 32) / 32.0;
             const double tile = (double)(c.TB * c.TL);
-            const double per_j = 5.0 * tile + (c.TB + 1) / 2 + (c.TL + 1) / 2 + c.TL;  // issue slots per j
-            const double combine = 12.0 * js / (double)((t.K + js - 1) / js);          // per cell, amortised
-            const double eff = lanes * rows_eff * lev_eff * (5.0 * tile) / (per_j + combine * tile / 5.0);
-            const double par = (double)c.G * c.threads;  // parallel lanes in flight
-            double score = eff * (par < 148.0 * 128 ? par / (148.0 * 128) : 1.0);
-            if (c.threads >= 256) score *= 1.02;  // two warps per scheduler hide barrier bubbles
+            const double per_j = 7.0 * tile + 2.0 * c.TL + ((c.TB + 1) / 2) + ((c.TL + 1) / 2) + 3.0;
+            const double b_cycles = per_j * c.jper * (double)(((int)warps + 3) / 4) * 1.25;
+            const double units = (double)c.R * (t.Kp / 32);
+            const double batches = (double)(((int)units + (int)warps * 4 - 1) / ((int)warps * 4));
+            const double c_cycles = batches * (1500.0 + 300.0 * js);
+            const double stage = b_cycles + c_cycles + 600.0;
+            const double score = 1.0 / stage;  // every CTA does the same work per stage: smaller is better
             if (score > best_score) { best_score = score; cfg = c; found = true; }
         }
     }
     return found;
 }
 
-template <int TB, int TL>
+template <int TB, int TL, int MAXT>
 static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, int argw, cudaStream_t st)
 {
     void *args[] = {(void *)&t, (void *)&cfg};
-    const void *fn = (argw == 1) ? (const void *)wavefront_kernel<TB, TL, uint8_t>
-                                 : (const void *)wavefront_kernel<TB, TL, uint16_t>;
+    const void *fn = (argw == 1) ? (const void *)wavefront_kernel<TB, TL, uint8_t, MAXT>
+                                 : (const void *)wavefront_kernel<TB, TL, uint16_t, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     // cooperative launch: the CTAs wait on one another, so all of them must be co-resident
@@ -466,12 +578,13 @@ static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, int argw,
 cudaError_t launch_wavefront(const Tables &t, const WaveCfg &cfg, int argw, cudaStream_t st)
 {
     switch (cfg.variant) {
-        case 0: return launch_variant<7, 4>(t, cfg, argw, st);
-        case 1: return launch_variant<8, 4>(t, cfg, argw, st);
-        case 2: return launch_variant<4, 4>(t, cfg, argw, st);
-        case 3: return launch_variant<8, 2>(t, cfg, argw, st);
-        case 4: return launch_variant<8, 1>(t, cfg, argw, st);
-        case 5: return launch_variant<4, 1>(t, cfg, argw, st);
+        case 0: return launch_variant<7, 4, kWaveThreadsBig>(t, cfg, argw, st);
+        case 1: return launch_variant<8, 4, kWaveThreadsBig>(t, cfg, argw, st);
+        case 2: return launch_variant<4, 4, kWaveThreadsSmall>(t, cfg, argw, st);
+        case 3: return launch_variant<7, 2, kWaveThreadsSmall>(t, cfg, argw, st);
+        case 4: return launch_variant<8, 2, kWaveThreadsSmall>(t, cfg, argw, st);
+        case 5: return launch_variant<8, 1, kWaveThreadsSmall>(t, cfg, argw, st);
+        case 6: return launch_variant<4, 1, kWaveThreadsSmall>(t, cfg, argw, st);
         default: return cudaErrorInvalidValue;
     }
 }

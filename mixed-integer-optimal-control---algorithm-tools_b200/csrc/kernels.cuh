@@ -32,6 +32,7 @@ struct WaveCfg {
     unsigned long long *flags;   // [G * kFlagStride]
     int *err;                    // [4]: inexact, stale, watchdog, abort
     const int *btmax;
+    long long *prof;             // optional [G][16] cycle counters (NULL = off)
 };
 
 // Fills the geometry fields of cfg for the given tables; returns false when the shape cannot run on the

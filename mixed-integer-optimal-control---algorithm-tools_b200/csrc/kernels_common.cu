@@ -24,20 +24,27 @@ __global__ void prep_kernel(Tables t, SlotDev slot, int *err, int *btmax)
     for (long long x = gtid; x < 2ll * t.B1 * t.Kp; x += nthr) slot.phi[x] = inf;
     unsigned long long upd = 0ull;
     int bad = 0, mx = 0;
-    for (long long row = gtid; row < t.n; row += nthr) {
+    // one thread per (stage row, level): stage cost and budget use of every stage (S3), kept for both kernel paths
+    for (long long x = gtid; x < (long long)t.n * t.Kp; x += nthr) {
+        const long long row = x / t.Kp;
+        const int l = (int)(x - row * t.Kp);
         const double *uo = slot.u_old + row * t.M;
-        for (int m = 0; m < t.M; ++m) {
-            const double v = uo[m];
-            if (!(fabs(v) <= 1073741824.0) || v != floor(v)) bad = 1;
+        double s = 0.;
+        int bt = t.B1;
+        if (l < t.K) {
+            stage_cost(t, t.lvd + l * t.M, slot.df + row * t.M, uo, s, bt);
+            if (bt < t.B1) {
+                if (row < t.n - 1) upd += (unsigned long long)(t.B1 - bt) * (unsigned long long)t.K;
+                mx = max(mx, bt);
+            }
         }
-        long long reach = 0;
-        for (int l = 0; l < t.K; ++l) {
-            double b = 0.;
-            for (int m = 0; m < t.M; ++m) b += fabs(t.lvd[l * t.M + m] - uo[m]);
-            const int bt = (b < (double)t.B1) ? (int)b : t.B1;
-            if (bt < t.B1) { reach += t.B1 - bt; mx = max(mx, bt); }
-        }
-        if (row < t.n - 1) upd += (unsigned long long)reach * (unsigned long long)t.K;
+        slot.ss_all[x] = s;
+        slot.bt_all[x] = bt;
+        if (l == 0)
+            for (int m = 0; m < t.M; ++m) {
+                const double v = uo[m];
+                if (!(fabs(v) <= 1073741824.0) || v != floor(v)) bad = 1;
+            }
     }
     atomicAdd(&s_upd, upd);
     if (bad) atomicOr(&s_bad, 1);
@@ -62,8 +69,8 @@ __global__ void terminal_kernel(Tables t, SlotDev slot, int pslot)
     const int b = blockIdx.x * blockDim.y + threadIdx.y;
     if (l >= t.K || b >= t.B1) return;
     const long long row = t.n - 1;
-    double s; int bt;
-    stage_cost(t, t.lvd + l * t.M, slot.df + row * t.M, slot.u_old + row * t.M, s, bt);
+    const double s = slot.ss_all[row * t.Kp + l];
+    const int bt = slot.bt_all[row * t.Kp + l];
     slot.phi[((long long)pslot * t.B1 + b) * t.Kp + l] = (b == bt) ? s : d_inf();
 }
 
@@ -76,8 +83,8 @@ __global__ void stage_kernel(Tables t, SlotDev slot, int i /* 1-based stage */)
     if (l >= t.K || bsrc >= t.B1) return;
     const int cur = (i + 1) & 1, nxt = i & 1;  // slot(i) = (i+1)%2 0-based, slot(i+1) = i%2
     const long long row = i - 1;
-    double s; int bt;
-    stage_cost(t, t.lvd + l * t.M, slot.df + row * t.M, slot.u_old + row * t.M, s, bt);
+    const double s = slot.ss_all[row * t.Kp + l];
+    const int bt = slot.bt_all[row * t.Kp + l];
     double *pc = slot.phi + (long long)cur * t.B1 * t.Kp;
     const double *pn = slot.phi + ((long long)nxt * t.B1 + bsrc) * t.Kp;
     if (bsrc < bt) pc[(long long)bsrc * t.Kp + l] = d_inf();  // target rows nobody reaches (:47)
@@ -258,9 +265,9 @@ __global__ void tv_kernel(Tables t, SlotDev slot, int mode /*0 = Inf, 1, 2*/, do
 void launch_prep(const Tables &t, const SlotDev &slot, int *err, int *btmax, cudaStream_t st)
 {
     const int threads = 256;
-    long long work = t.n > 2ll * t.B1 * t.Kp / 64 ? t.n : 2ll * t.B1 * t.Kp / 64;
-    int blocks = (int)((work + threads - 1) / threads);
-    if (blocks > 592) blocks = 592;
+    long long work = (long long)t.n * t.Kp > 2ll * t.B1 * t.Kp ? (long long)t.n * t.Kp : 2ll * t.B1 * t.Kp;
+    int blocks = (int)((work / 4 + threads - 1) / threads);
+    if (blocks > 1184) blocks = 1184;
     if (blocks < 1) blocks = 1;
     prep_kernel<<<blocks, threads, 0, st>>>(t, slot, err, btmax);
 }

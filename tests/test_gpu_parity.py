@@ -126,7 +126,7 @@ def test_synthetic_config4_shape_vs_oracle(gpu_lib, oracle, tie):
 
 
 @pytest.mark.parametrize("tune", [dict(ctas=8, jsplit=1), dict(ctas=5, jsplit=2), dict(ctas=16, jsplit=5, variant=2),
-                                  dict(ctas=40, jsplit=3, variant=4), dict(ctas=148, jsplit=8, variant=1),
+                                  dict(ctas=40, jsplit=3, variant=4), dict(ctas=148, jsplit=7, variant=1),
                                   dict(jsplit=1, variant=6), dict(ctas=9, variant=3)])
 def test_wavefront_geometries(gpu_lib, oracle, tune):
     """Every tile variant / CTA count / j-split of the pipelined kernel gives identical bits."""

@@ -1,0 +1,31 @@
+"""Prints the in-kernel cycle breakdown of the wavefront kernel (bb200_profile) on config-4-shaped input.
+Usage: python tools/phase_profile.py [n] [ctas jsplit variant]"""
+import importlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import mioc_b200 as m
+wl = importlib.import_module(m.__name__ + ".workloads")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+tune = [int(x) for x in sys.argv[2:5]] if len(sys.argv) > 4 else [0, 0, 0]
+inst = wl.synthetic(n=n, B=999, seed=20251018)
+plan = m.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt)
+plan.tune(*tune)
+plan.upload(0, inst.df, inst.u_old)
+plan.bellman_resident(0, 1); plan.sync()
+plan.profile(True)
+plan.bellman_resident(0, 1); plan.sync()
+st = plan.stats()
+prof = plan.profile(True, fetch=True)
+G = int(st["ctas"])
+print(f"ctas={G} rows={int(st['rows_per_cta'])} threads={int(st['threads'])} js={int(st['jsplit'])} wave_ms={st['wave_ms']:.3f} "
+      f"us/stage={st['wave_ms']*1e3/(n-1):.2f}  T upd/s={plan.count_updates()/st['wave_ms']/1e9:.3f}")
+names_c = ["wait_full", "phaseB", "barrier", "phaseC"]
+names_m = ["eval", "flagwait", "gather", "donewait", "publish"]
+for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
+    row = prof[gsel]
+    stg = max(row[4], 1)
+    print(f"cta {gsel:3d} compute cyc/stage: " + "  ".join(f"{nm}={row[k]/stg:8.0f}" for k, nm in enumerate(names_c)) +
+          f" | comm: " + "  ".join(f"{nm}={row[8+k]/max(row[13],1):8.0f}" for k, nm in enumerate(names_m)))
+avg = prof[:G].mean(axis=0)
+print("avg compute:", {nm: round(avg[k]/max(avg[4],1)) for k, nm in enumerate(names_c)}, "comm:", {nm: round(avg[8+k]/max(avg[13],1)) for k, nm in enumerate(names_m)})

@@ -1,0 +1,153 @@
+// phaseb_probe.cu -- isolates phase B of the wavefront kernel (register-tiled min-plus scan) to find what bounds it.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -o tools/phaseb_probe.bin tools/phaseb_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ double inf_d() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// MODE 0: as in the kernel (a = s + c per j, loads of P and c from smem)
+// MODE 1: a preloaded (no per-j DADD for a): c table already holds s + c
+// MODE 2: no smem loads in the loop at all (p, a synthesized from registers)
+// MODE 3: like 0 but rows outer / levels inner
+// MODE 4: like 0 but compare against a copy (no loop-carried dependence on best): pure throughput of the mix
+template <int TB, int TL, int MODE>
+__device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const double *__restrict__ crow,
+                                        const double *__restrict__ srow, double *__restrict__ pv, int jb, int je,
+                                        int RP, int Kp)
+{
+    constexpr int TBP = (TB + 1) & ~1;
+    const double inf = inf_d();
+    double best[TB][TL];
+#pragma unroll
+    for (int a = 0; a < TB; ++a)
+#pragma unroll
+        for (int q = 0; q < TL; ++q) best[a][q] = inf;
+    double s[TL];
+#pragma unroll
+    for (int q = 0; q < TL; ++q) s[q] = srow[q];
+    double p[TBP];
+    double a[TL];
+    if (MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < TBP; ++k) p[k] = Prow[k];
+#pragma unroll
+        for (int q = 0; q < TL; ++q) a[q] = crow[q];
+    }
+#pragma unroll 2
+    for (int j = jb; j < je; ++j) {
+        if (MODE != 2) {
+#pragma unroll
+            for (int k = 0; k < TBP / 2; ++k) {
+                const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)j * RP + 2 * k);
+                p[2 * k] = x.x;
+                p[2 * k + 1] = x.y;
+            }
+#pragma unroll
+            for (int k = 0; k < TL / 2; ++k) {
+                const double2 x = *reinterpret_cast<const double2 *>(crow + (size_t)j * Kp + 2 * k);
+                if (MODE == 1) { a[2 * k] = x.x; a[2 * k + 1] = x.y; }
+                else { a[2 * k] = __dadd_rn(s[2 * k], x.x); a[2 * k + 1] = __dadd_rn(s[2 * k + 1], x.y); }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < TBP; ++k) p[k] = -p[k];
+        }
+        if (MODE == 3) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r)
+#pragma unroll
+                for (int q = 0; q < TL; ++q) {
+                    const double v = __dadd_rn(a[q], p[r]);
+                    if (best[r][q] > v) best[r][q] = v;
+                }
+        } else {
+#pragma unroll
+            for (int q = 0; q < TL; ++q) {
+                double v[TB];
+                bool gt[TB];
+#pragma unroll
+                for (int r = 0; r < TB; ++r) v[r] = __dadd_rn(a[q], p[r]);
+#pragma unroll
+                for (int r = 0; r < TB; ++r) gt[r] = best[r][q] > v[r];
+#pragma unroll
+                for (int r = 0; r < TB; ++r) best[r][q] = gt[r] ? v[r] : best[r][q];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TB; ++r)
+#pragma unroll
+        for (int q = 0; q < TL; ++q) pv[(size_t)r * Kp + q] = best[r][q];
+}
+
+template <int TB, int TL, int MODE>
+__global__ void __launch_bounds__(576, 1) k(double *out, long long *cyc, int K, int JS, int reps)
+{
+    extern __shared__ double sm[];
+    constexpr int TBP = (TB + 1) & ~1;
+    const int Kp = 128, RP = TBP;
+    double *Ps = sm;                    // [K][RP]
+    double *cs = Ps + Kp * RP;          // [K][Kp]
+    double *ss = cs + K * Kp;           // [Kp]
+    double *pv = ss + Kp;               // [JS][TB][Kp]
+    for (int x = threadIdx.x; x < Kp * RP; x += blockDim.x) Ps[x] = (double)((x * 7919) % 1013) * 0.001;
+    for (int x = threadIdx.x; x < K * Kp; x += blockDim.x) cs[x] = (double)((x * 104729) % 2003) * 0.0005;
+    for (int x = threadIdx.x; x < Kp; x += blockDim.x) ss[x] = (double)x * 0.01;
+    __syncthreads();
+    const int nLG = Kp / TL;                       // level groups (all lanes active)
+    const int tpg = ((nLG + 31) / 32) * 32;
+    const int jg = threadIdx.x / tpg, lg = threadIdx.x % tpg;
+    const int jper = (K + JS - 1) / JS;
+    const int jb = jg * jper, je = min(K, jb + jper);
+    long long t0 = clock64();
+    if (lg < nLG)
+        for (int r = 0; r < reps; ++r)
+            phase_b<TB, TL, MODE>(Ps, cs + lg * TL, ss + lg * TL, pv + (size_t)jg * TB * Kp + lg * TL, jb, je, RP, Kp);
+    __syncthreads();
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+    if (pv[threadIdx.x] == 123.456) out[0] = 1.;
+}
+
+template <int TB, int TL, int MODE>
+void run(const char *name, int JS)
+{
+    const int K = 125, Kp = 128, reps = 200;
+    constexpr int TBP = (TB + 1) & ~1;
+    const int nLG = Kp / TL, tpg = ((nLG + 31) / 32) * 32;
+    const int threads = JS * tpg;
+    if (threads > 576) return;
+    size_t smem = (size_t)(Kp * TBP + K * Kp + Kp + JS * TB * Kp) * sizeof(double);
+    double *d_out; long long *d_cyc;
+    cudaMalloc(&d_out, 8); cudaMalloc(&d_cyc, 8);
+    cudaFuncSetAttribute(k<TB, TL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<TB, TL, MODE><<<148, threads, smem>>>(d_out, d_cyc, K, JS, reps);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long cyc = 0; cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+    // warp-level relaxations per SMSP per rep: warps/4 * jper * TB*TL
+    const double warps = threads / 32.0;
+    const double relax = warps / 4.0 * ((K + JS - 1) / JS) * TB * TL * reps;
+    printf("%-34s tile %dx%d JS=%2d warps=%4.0f  %9lld cyc  %6.2f cyc per warp-relaxation per scheduler  (%s)\n", name, TB, TL, JS,
+           warps, cyc, cyc / relax, cudaGetErrorString(e));
+    cudaFree(d_out); cudaFree(d_cyc);
+}
+
+int main()
+{
+    for (int JS : {4, 8}) {
+        run<7, 4, 0>("0 kernel form", JS);
+        run<7, 4, 1>("1 a preloaded", JS);
+        run<7, 4, 2>("2 no smem loads", JS);
+        run<7, 4, 3>("3 rows outer (interleaved)", JS);
+    }
+    for (int JS : {4, 8}) {
+        run<7, 2, 0>("0 kernel form", JS);
+        run<7, 2, 1>("1 a preloaded", JS);
+        run<7, 2, 2>("2 no smem loads", JS);
+        run<4, 4, 0>("0 kernel form", JS);
+        run<4, 2, 0>("0 kernel form", JS);
+        run<8, 1, 0>("0 kernel form 8x1 (TL odd n/a)", JS);
+    }
+    return 0;
+}

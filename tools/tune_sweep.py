@@ -17,8 +17,8 @@ inst = wl.synthetic(n=n, B=999, seed=20251018)
 plan = m.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt)
 plan.upload(0, inst.df, inst.u_old)
 rows = []
-variants = {1: "7x4", 2: "8x4", 3: "4x4", 4: "8x2", 5: "8x1", 6: "4x1"}
-combos = list(itertools.product([1, 2, 3, 4, 5], [1, 2, 3, 4, 6, 8], [0]))
+variants = {1: "7x4", 2: "8x4", 3: "4x4", 4: "7x2", 5: "8x2", 6: "8x1", 7: "4x1"}
+combos = list(itertools.product([1, 2, 3, 4, 5, 6], [2, 4, 6, 7, 8], [0]))
 for v, js, ctas in combos:
     try:
         plan.tune(ctas, js, v)
