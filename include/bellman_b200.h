@@ -164,6 +164,7 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *   6 argmin bytes per cell (1 or 2)           7 device bytes owned by the plan
  *   8 threads per CTA of the last DP launch    9 j-split of the last DP launch
  *  10 device time [ms] of the last persistent wavefront kernel alone (events around that launch)
+ *  11 number of CUDA-graph replays performed by bb200_solve
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);
 

@@ -81,6 +81,12 @@ struct bb200_plan {
     // pinned staging
     double *h_rec = nullptr;
     int *h_err = nullptr;
+    // CUDA-graph replay of one TR iteration (bb200_solve): pinned input/output staging + the captured graph
+    double *h_df = nullptr, *h_uold = nullptr, *h_u = nullptr;
+    int *h_bnew = nullptr, *d_bnew = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_failed = false;
+    double graph_replays = 0.;
     // geometry
     int num_sms = 0;
     size_t smem_max = 0;
@@ -137,16 +143,22 @@ void destroy_plan(bb200_plan *p)
     cudaFree(p->d_prof);
     if (p->h_rec) cudaFreeHost(p->h_rec);
     if (p->h_err) cudaFreeHost(p->h_err);
+    if (p->h_df) cudaFreeHost(p->h_df);
+    if (p->h_uold) cudaFreeHost(p->h_uold);
+    if (p->h_u) cudaFreeHost(p->h_u);
+    if (p->h_bnew) cudaFreeHost(p->h_bnew);
+    cudaFree(p->d_bnew);
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
 }
 
 // Queue the DP for slots [slot0, slot0+count) on the plan's stream.
-int queue_dp(bb200_plan *p, int slot0, int count)
+int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false)
 {
     cudaStream_t st = p->stream;
-    CU(cudaEventRecord(p->ev[0], st));
+    if (!capturing) CU(cudaEventRecord(p->ev[0], st));
     CU(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(int), st));
     CU(cudaMemsetAsync(p->d_btmax, 0, sizeof(int), st));
     for (int s = slot0; s < slot0 + count; ++s) {
@@ -165,9 +177,9 @@ int queue_dp(bb200_plan *p, int slot0, int count)
         c.err = p->d_err;
         c.btmax = p->d_btmax;
         c.prof = p->prof_on ? p->d_prof : nullptr;
-        CU(cudaEventRecord(p->ev[4], st));
+        if (!capturing) CU(cudaEventRecord(p->ev[4], st));
         CU(launch_wavefront(p->tab, c, p->argw, st));
-        CU(cudaEventRecord(p->ev[5], st));
+        if (!capturing) CU(cudaEventRecord(p->ev[5], st));
         p->launches += 1;
         p->last_path = 1;
     } else {
@@ -178,28 +190,76 @@ int queue_dp(bb200_plan *p, int slot0, int count)
         }
         p->last_path = 0;
     }
+    if (capturing) return BB200_OK;
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[1], st));
     p->dp_timed = true;
     return BB200_OK;
 }
 
-int queue_backtrack(bb200_plan *p, int slot, int64_t B_new, int rec_idx)
+int queue_backtrack(bb200_plan *p, int slot, int64_t B_new, int rec_idx, bool capturing = false)
 {
     if (!p->slots[slot].has_dp) return fail(BB200_ERR_STATE, "slot %d has no DP result yet", slot);
     if (B_new < 0 || B_new > p->B) return fail(BB200_ERR_ARG, "B_new=%lld outside [0, %lld]", (long long)B_new, (long long)p->B);
     cudaStream_t st = p->stream;
     SlotDev sd = p->slots_dev[slot];
     sd.rec = p->slots[slot].rec + 4 * rec_idx;
-    CU(cudaEventRecord(p->ev[2], st));
+    if (!capturing) CU(cudaEventRecord(p->ev[2], st));
     CU(cudaMemsetAsync(p->d_err + 1, 0, sizeof(int), st));  // the stale flag is per selection
-    launch_select(p->tab, sd, (int)B_new, p->d_err, st);
+    launch_select(p->tab, sd, (int)B_new, capturing ? p->d_bnew : nullptr, p->d_err, st);
     launch_backtrack(p->tab, sd, p->argw, p->d_err, st);
     p->launches += 2;
+    if (capturing) return BB200_OK;
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[3], st));
     p->bt_timed = true;
     return BB200_OK;
+}
+
+// Captures one TR inner iteration of slot 0 -- H2D(df, u_old, B') -> prep -> DP -> selection -> backtrack ->
+// D2H(u, optimum, error word) -- into a CUDA graph (multi-trust.jl:112-113 as one replayable unit).  All shapes
+// are fixed for a TRM run, the trial budget travels through device memory.  Returns false when the
+// capture is not possible (then bb200_solve launches directly).
+bool ensure_graph(bb200_plan *p)
+{
+    if (p->graph_exec) return true;
+    if (p->graph_failed || (p->flags & BB200_FLAG_NO_GRAPH)) return false;
+    const size_t io = (size_t)p->n * p->M * sizeof(double);
+    if (!p->h_df) {
+        if (cudaMallocHost((void **)&p->h_df, io) != cudaSuccess || cudaMallocHost((void **)&p->h_uold, io) != cudaSuccess ||
+            cudaMallocHost((void **)&p->h_u, io) != cudaSuccess || cudaMallocHost((void **)&p->h_bnew, sizeof(int)) != cudaSuccess ||
+            cudaMalloc((void **)&p->d_bnew, sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            p->graph_failed = true;
+            return false;
+        }
+    }
+    cudaStream_t st = p->stream;
+    cudaGraph_t graph = nullptr;
+    const double launches_before = p->launches;
+    const bool had_dp = p->slots[0].has_dp;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        ok = cudaMemcpyAsync(p->slots[0].df, p->h_df, io, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+             cudaMemcpyAsync(p->slots[0].u_old, p->h_uold, io, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+             cudaMemcpyAsync(p->d_bnew, p->h_bnew, sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+             queue_dp(p, 0, 1, true) == BB200_OK && queue_backtrack(p, 0, p->B, 0, true) == BB200_OK &&
+             cudaMemcpyAsync(p->h_u, p->slots[0].u, io, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaMemcpyAsync(p->h_rec, p->slots[0].rec, 4 * sizeof(double), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaMemcpyAsync(p->h_err, p->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        ok = ok && e == cudaSuccess && graph != nullptr;
+    }
+    p->launches = launches_before;  // capture launches nothing
+    p->slots[0].has_dp = had_dp;
+    if (ok) ok = cudaGraphInstantiate(&p->graph_exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();
+        p->graph_exec = nullptr;
+        p->graph_failed = true;
+    }
+    return ok;
 }
 
 // Synchronise and translate the deferred device-side error word.
@@ -479,11 +539,38 @@ int bb200_select_and_backtrack(bb200_plan *plan, int64_t B_new, double *u_out, d
 int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t B_new, double *u_out,
                 double *phi_star, int64_t *b_star, int64_t *k_star)
 {
-    int rc = bb200_upload(plan, 0, df, u_old);
-    if (rc) return rc;
-    if (!u_out) return fail(BB200_ERR_ARG, "u_out is NULL");
+    if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
+    if (!df || !u_old || !u_out) return fail(BB200_ERR_ARG, "df/u_old/u_out is NULL");
+    if (B_new < 0 || B_new > plan->B) return fail(BB200_ERR_ARG, "B_new=%lld outside [0, %lld]", (long long)B_new, (long long)plan->B);
     Guard g(plan);
-    rc = queue_dp(plan, 0, 1);
+    const size_t io = (size_t)plan->n * plan->M * sizeof(double);
+    if (ensure_graph(plan)) {
+        // replay: stage the inputs in pinned memory, one graph launch, one synchronisation
+        std::memcpy(plan->h_df, df, io);
+        std::memcpy(plan->h_uold, u_old, io);
+        *plan->h_bnew = (int)B_new;
+        CU(cudaEventRecord(plan->ev[0], plan->stream));
+        CU(cudaGraphLaunch(plan->graph_exec, plan->stream));
+        CU(cudaEventRecord(plan->ev[1], plan->stream));
+        CU(cudaStreamSynchronize(plan->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, plan->ev[0], plan->ev[1]) == cudaSuccess) plan->last_dp_ms = ms;
+        plan->slots[0].has_dp = true;
+        plan->launches += 4 + (plan->wave_ok ? 0 : (double)plan->n - 1);  // prep, DP, selection, backtrack
+        plan->last_path = plan->wave_ok ? 1 : 0;
+        plan->graph_replays += 1;
+        std::memcpy(u_out, plan->h_u, io);
+        if (phi_star) *phi_star = plan->h_rec[0];
+        if (b_star) *b_star = (int64_t)plan->h_rec[1];
+        if (k_star) *k_star = (int64_t)plan->h_rec[2];
+        if (plan->h_err[2]) return fail(BB200_ERR_CUDA, "wavefront kernel watchdog fired: a pipeline dependency was never satisfied");
+        if (plan->h_err[0]) return fail(BB200_ERR_INEXACT, "InexactError: u_old is not integer valued / finite (HelpFunctions.jl:37,57)");
+        if (plan->h_err[1]) return fail(BB200_ERR_STALE, "selection/backtrack reached a cell the DP never wrote (no feasible trajectory for this u_old / budget)");
+        return BB200_OK;
+    }
+    CU(cudaMemcpyAsync(plan->slots[0].df, df, io, cudaMemcpyHostToDevice, plan->stream));
+    CU(cudaMemcpyAsync(plan->slots[0].u_old, u_old, io, cudaMemcpyHostToDevice, plan->stream));
+    int rc = queue_dp(plan, 0, 1);
     if (rc) return rc;
     rc = queue_backtrack(plan, 0, B_new, 0);
     if (rc) return rc;
@@ -685,12 +772,12 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
 {
     if (!plan || !out) return fail(BB200_ERR_ARG, "bad arguments");
     Guard g(plan);
-    const double v[11] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+    const double v[12] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
                           plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
                           (double)plan->argw, (double)plan->dev_bytes,
                           plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.,
-                          plan->last_wave_ms};
-    for (int k = 0; k < count && k < 11; ++k) out[k] = v[k];
+                          plan->last_wave_ms, plan->graph_replays};
+    for (int k = 0; k < count && k < 12; ++k) out[k] = v[k];
     return BB200_OK;
 }
 

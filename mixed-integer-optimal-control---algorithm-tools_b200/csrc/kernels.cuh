@@ -7,7 +7,7 @@ namespace bb200 {
 // kernels_common.cu
 void launch_prep(const Tables &t, const SlotDev &slot, int *err, int *btmax, cudaStream_t st);
 int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream_t st);
-void launch_select(const Tables &t, const SlotDev &slot, int Bnew, int *err, cudaStream_t st);
+void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bnew_ptr, int *err, cudaStream_t st);
 void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st);
 void launch_pred_integral(const Tables &t, const SlotDev &slot, double *out, cudaStream_t st);
 void launch_tv(const Tables &t, const SlotDev &slot, int mode, double *out, cudaStream_t st);

@@ -115,8 +115,12 @@ __device__ __forceinline__ bool cand_precedes(const Cand &x, const Cand &y)
     return x.pos < y.pos;
 }
 
-__global__ void select_kernel(Tables t, SlotDev slot, int Bnew, int *err)
+__global__ void select_kernel(Tables t, SlotDev slot, int Bnew_arg, const int *bnew_ptr, int *err)
 {
+    // the graph-replayed path passes the trial budget through device memory so that one captured graph serves every B'
+    int Bnew = bnew_ptr ? *bnew_ptr : Bnew_arg;
+    if (Bnew < 0) Bnew = 0;
+    if (Bnew > t.B1 - 1) Bnew = t.B1 - 1;
     __shared__ Cand s_c[32];
     Cand best;
     best.v = d_inf(); best.pos = 0x7fffffffffffffffLL; best.k = -1; best.b = -1;
@@ -163,31 +167,81 @@ __global__ void select_kernel(Tables t, SlotDev slot, int Bnew, int *err)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backtrack (HelpFunctions.jl:108-122): a dependent chase of n-1 argmin bytes.  With the source-row
+// Backtrack (HelpFunctions.jl:108-122): a dependent chase of n-1 argmin entries.  With the source-row
 // indexed table one step is  b' = b - b~_l(i);  l <- arg[i-1][b'][l];  b <- b'.
-// One warp: lane 0 chases; all lanes prefetch the next rows' neighbourhood into L2/L1.
+// The budget only shrinks along the trajectory and by at most max b~ per stage, so the entries the chase
+// can touch in the next S stages lie in a window of W budget rows below the current b.  The CTA streams that
+// window (S x W x Kp entries, contiguous per stage) and the stages' budget uses into shared memory with
+// coalesced 16-byte loads, one thread chases through shared memory (two dependent LDS per stage instead of
+// two dependent HBM reads), then all threads write the S controls.  If the budget leaves the window the
+// chunk ends early and the window is re-centred.
 // ------------------------------------------------------------------------------------------------
 template <typename ArgT>
-__global__ void backtrack_kernel(Tables t, SlotDev slot, int *err)
+__global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev slot, int *err, int S, int W)
 {
     constexpr ArgT MARK = (ArgT)~(ArgT)0;
+    extern __shared__ __align__(16) unsigned char smem_bt[];
+    ArgT *win = reinterpret_cast<ArgT *>(smem_bt);                                   // [S][W][Kp]
+    int *bts = reinterpret_cast<int *>(smem_bt + (size_t)S * W * t.Kp * sizeof(ArgT));  // [S][Kp]
+    int *lseq = bts + (size_t)S * t.Kp;                                              // [S]
+    __shared__ int s_b, s_l, s_done, s_fail;
     if (slot.rec[3] != 0.) return;
-    if (threadIdx.x != 0) return;
-    int b = (int)slot.rec[1];
-    int l = (int)slot.rec[2];
+    const int tid = threadIdx.x, NT = blockDim.x;
     const ArgT *arg = reinterpret_cast<const ArgT *>(slot.arg);
-    for (int m = 0; m < t.M; ++m) slot.u[m] = t.lvd[l * t.M + m];
-    for (long long i = 1; i <= t.n - 1; ++i) {
-        const double *uo = slot.u_old + (i - 1) * t.M;
-        double d = 0.;
-        for (int m = 0; m < t.M; ++m) d += fabs(t.lvd[l * t.M + m] - uo[m]);
-        const int bsrc = b - (int)d;
-        if (bsrc < 0) { atomicOr(&err[1], 1); slot.rec[3] = 1.; return; }
-        const ArgT a = arg[((i - 1) * t.B1 + bsrc) * t.Kp + l];
-        if (a == MARK || (int)a >= t.K) { atomicOr(&err[1], 1); slot.rec[3] = 1.; return; }
-        l = (int)a;
-        b = bsrc;
-        for (int m = 0; m < t.M; ++m) slot.u[i * t.M + m] = t.lvd[l * t.M + m];
+    if (tid == 0) {
+        s_b = (int)slot.rec[1];
+        s_l = (int)slot.rec[2];
+        s_fail = 0;
+    }
+    __syncthreads();
+    for (int m = tid; m < t.M; m += NT) slot.u[m] = t.lvd[s_l * t.M + m];  // u[:,1] (:108-112)
+    const int row_vecs = (int)((size_t)W * t.Kp * sizeof(ArgT) / 16);  // 16-byte vectors per stage window
+    for (long long i0 = 1; i0 <= t.n - 1;) {
+        const int cnt = (int)min((long long)S, t.n - i0);  // stages i0 .. i0+cnt-1
+        const int b0 = s_b;
+        int wb = b0 - W + 1;
+        if (wb < 0) wb = 0;
+        const int wrows = min(W, t.B1 - wb);
+        // ---- stream the window and the budget uses of these stages into shared memory -------------------
+        for (int x = tid; x < cnt * row_vecs; x += NT) {
+            const int st = x / row_vecs, v = x - st * row_vecs;
+            if ((size_t)v * 16 < (size_t)wrows * t.Kp * sizeof(ArgT)) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(arg + ((size_t)(i0 + st - 1) * t.B1 + wb) * t.Kp);
+                reinterpret_cast<uint4 *>(win + (size_t)st * W * t.Kp)[v] = __ldcs(src + v);
+            }
+        }
+        for (int x = tid; x < cnt * t.Kp; x += NT) bts[x] = slot.bt_all[(size_t)(i0 - 1) * t.Kp + x];
+        __syncthreads();
+        // ---- chase through shared memory -----------------------------------------------------------------
+        if (tid == 0) {
+            int b = b0, l = s_l, st = 0, fail = 0;
+            for (; st < cnt; ++st) {
+                const int bsrc = b - bts[st * t.Kp + l];
+                if (bsrc < 0) { fail = 1; break; }     // unreachable level: the reference would read stale U
+                if (bsrc < wb && st > 0) break;        // left the window: re-centre
+                // (a first step that jumps below the window reads its one entry straight from HBM)
+                const ArgT a = (bsrc >= wb) ? win[((size_t)st * W + (bsrc - wb)) * t.Kp + l]
+                                            : arg[((size_t)(i0 + st - 1) * t.B1 + bsrc) * t.Kp + l];
+                if (a == MARK || (int)a >= t.K) { fail = 1; break; }
+                l = (int)a;
+                b = bsrc;
+                lseq[st] = l;
+            }
+            s_b = b; s_l = l; s_done = st; s_fail = fail;
+        }
+        __syncthreads();
+        const int done = s_done;
+        // ---- u[:, i+1] = nu_l for the stages walked (:117-119) ---------------------------------------------
+        for (int x = tid; x < done * t.M; x += NT) {
+            const int st = x / t.M, m = x - st * t.M;
+            slot.u[(size_t)(i0 + st) * t.M + m] = t.lvd[lseq[st] * t.M + m];
+        }
+        if (s_fail) {
+            if (tid == 0) { atomicOr(&err[1], 1); slot.rec[3] = 1.; }
+            return;
+        }
+        i0 += done;  // done >= 1: the first step of a chunk always completes
+        __syncthreads();
     }
 }
 
@@ -292,15 +346,29 @@ int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream
     return launches;
 }
 
-void launch_select(const Tables &t, const SlotDev &slot, int Bnew, int *err, cudaStream_t st)
+void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bnew_ptr, int *err, cudaStream_t st)
 {
-    select_kernel<<<1, 1024, 0, st>>>(t, slot, Bnew, err);
+    select_kernel<<<1, 1024, 0, st>>>(t, slot, Bnew, bnew_ptr, err);
 }
 
 void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st)
 {
-    if (argw == 1) backtrack_kernel<uint8_t><<<1, 32, 0, st>>>(t, slot, err);
-    else backtrack_kernel<uint16_t><<<1, 32, 0, st>>>(t, slot, err);
+    // window rows W: at most 24 (a step that uses more budget than that falls back to one HBM read); stages per
+    // chunk S: whatever fits into ~200 KB of shared memory, at most 64
+    int W = t.B1 < 24 ? t.B1 : 24;
+    const size_t per_stage = (size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int);
+    long long S = (long long)(200 * 1024) / (long long)per_stage;
+    if (S > 64) S = 64;
+    if (S < 1) { S = 1; }
+    while (W > 1 && (size_t)S * ((size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int)) > 220 * 1024) --W;
+    const size_t smem = (size_t)S * ((size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int)) + 16;
+    if (argw == 1) {
+        cudaFuncSetAttribute(backtrack_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        backtrack_kernel<uint8_t><<<1, 1024, smem, st>>>(t, slot, err, (int)S, W);
+    } else {
+        cudaFuncSetAttribute(backtrack_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        backtrack_kernel<uint16_t><<<1, 1024, smem, st>>>(t, slot, err, (int)S, W);
+    }
 }
 
 void launch_pred_integral(const Tables &t, const SlotDev &slot, double *out, cudaStream_t st)
