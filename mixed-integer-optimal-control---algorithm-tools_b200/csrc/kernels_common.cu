@@ -170,9 +170,9 @@ __global__ void select_kernel(Tables t, SlotDev slot, int Bnew_arg, const int *b
 // Backtrack (HelpFunctions.jl:108-122): a dependent chase of n-1 argmin entries.  With the source-row
 // indexed table one step is  b' = b - b~_l(i);  l <- arg[i-1][b'][l];  b <- b'.
 // The budget only shrinks along the trajectory and by at most max b~ per stage, so the entries the chase
-// can touch in the next S stages lie in a window of W budget rows below the current b.  The CTA streams that
-// window (S x W x Kp entries, contiguous per stage) and the stages' budget uses into shared memory with
-// coalesced 16-byte loads, one thread chases through shared memory (two dependent LDS per stage instead of
+// can touch in the next S stages lie in a window of W budget rows below the current b.  The CTA brings that
+// window (S x W x Kp entries, one contiguous block per stage) and the stages' budget uses into shared memory by
+// 1-D bulk TMA, one thread chases through shared memory (two dependent LDS per stage instead of
 // two dependent HBM reads), then all threads write the S controls.  If the budget leaves the window the
 // chunk ends early and the window is re-centred.
 // ------------------------------------------------------------------------------------------------
@@ -180,10 +180,11 @@ template <typename ArgT>
 __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev slot, int *err, int S, int W)
 {
     constexpr ArgT MARK = (ArgT)~(ArgT)0;
-    extern __shared__ __align__(16) unsigned char smem_bt[];
+    extern __shared__ __align__(128) unsigned char smem_bt[];
     ArgT *win = reinterpret_cast<ArgT *>(smem_bt);                                   // [S][W][Kp]
     int *bts = reinterpret_cast<int *>(smem_bt + (size_t)S * W * t.Kp * sizeof(ArgT));  // [S][Kp]
     int *lseq = bts + (size_t)S * t.Kp;                                              // [S]
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_b, s_l, s_done, s_fail;
     if (slot.rec[3] != 0.) return;
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -192,26 +193,30 @@ __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev sl
         s_b = (int)slot.rec[1];
         s_l = (int)slot.rec[2];
         s_fail = 0;
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     for (int m = tid; m < t.M; m += NT) slot.u[m] = t.lvd[s_l * t.M + m];  // u[:,1] (:108-112)
-    const int row_vecs = (int)((size_t)W * t.Kp * sizeof(ArgT) / 16);  // 16-byte vectors per stage window
+    uint32_t phase = 0;
     for (long long i0 = 1; i0 <= t.n - 1;) {
         const int cnt = (int)min((long long)S, t.n - i0);  // stages i0 .. i0+cnt-1
         const int b0 = s_b;
         int wb = b0 - W + 1;
         if (wb < 0) wb = 0;
         const int wrows = min(W, t.B1 - wb);
-        // ---- stream the window and the budget uses of these stages into shared memory -------------------
-        for (int x = tid; x < cnt * row_vecs; x += NT) {
-            const int st = x / row_vecs, v = x - st * row_vecs;
-            if ((size_t)v * 16 < (size_t)wrows * t.Kp * sizeof(ArgT)) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(arg + ((size_t)(i0 + st - 1) * t.B1 + wb) * t.Kp);
-                reinterpret_cast<uint4 *>(win + (size_t)st * W * t.Kp)[v] = __ldcs(src + v);
-            }
+        // ---- bulk-TMA the window (one contiguous block per stage) and the stages' budget uses into shared memory
+        if (tid < 32) {
+            const uint32_t wbytes = (uint32_t)((size_t)wrows * t.Kp * sizeof(ArgT));
+            if (tid == 0) mbar_expect_tx(&s_bar, (uint32_t)cnt * wbytes + (uint32_t)((size_t)cnt * t.Kp * sizeof(int)));
+            __syncwarp();
+            for (int st = tid; st < cnt; st += 32)
+                tma_load_1d(win + (size_t)st * W * t.Kp, arg + ((size_t)(i0 + st - 1) * t.B1 + wb) * t.Kp, wbytes, &s_bar);
+            if (tid == 0)
+                tma_load_1d(bts, slot.bt_all + (size_t)(i0 - 1) * t.Kp, (uint32_t)((size_t)cnt * t.Kp * sizeof(int)), &s_bar);
         }
-        for (int x = tid; x < cnt * t.Kp; x += NT) bts[x] = slot.bt_all[(size_t)(i0 - 1) * t.Kp + x];
-        __syncthreads();
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
         // ---- chase through shared memory -----------------------------------------------------------------
         if (tid == 0) {
             int b = b0, l = s_l, st = 0, fail = 0;
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev sl
             return;
         }
         i0 += done;  // done >= 1: the first step of a chunk always completes
-        __syncthreads();
+        __syncthreads();  // everyone is finished with the window before the next TMA overwrites it
     }
 }
 
@@ -361,7 +366,7 @@ void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, 
     if (S > 64) S = 64;
     if (S < 1) { S = 1; }
     while (W > 1 && (size_t)S * ((size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int)) > 220 * 1024) --W;
-    const size_t smem = (size_t)S * ((size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int)) + 16;
+    const size_t smem = (size_t)S * ((size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int)) + 128;
     if (argw == 1) {
         cudaFuncSetAttribute(backtrack_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         backtrack_kernel<uint8_t><<<1, 1024, smem, st>>>(t, slot, err, (int)S, W);
