@@ -452,6 +452,11 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     }
     if (c.prof && tid == 0)
         for (int k = 0; k < 5; ++k) c.prof[(size_t)g * 16 + k] = pc[k];
+    if (c.prof && tid == 32) {  // a warp on another scheduler than the comm warp's: B phase and barrier wait
+        c.prof[(size_t)g * 16 + 5] = pc[1];
+        c.prof[(size_t)g * 16 + 6] = pc[2];
+        c.prof[(size_t)g * 16 + 7] = pc[3];
+    }
 #undef PROF_LAP
 }
 

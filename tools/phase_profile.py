@@ -28,4 +28,5 @@ for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
     print(f"cta {gsel:3d} compute cyc/stage: " + "  ".join(f"{nm}={row[k]/stg:8.0f}" for k, nm in enumerate(names_c)) +
           f" | comm: " + "  ".join(f"{nm}={row[8+k]/max(row[13],1):8.0f}" for k, nm in enumerate(names_m)))
 avg = prof[:G].mean(axis=0)
+print("warp1 (other scheduler) cyc/stage: phaseB=%d barrier=%d phaseC=%d" % tuple(round(avg[k]/max(avg[4],1)) for k in (5,6,7)))
 print("avg compute:", {nm: round(avg[k]/max(avg[4],1)) for k, nm in enumerate(names_c)}, "comm:", {nm: round(avg[8+k]/max(avg[13],1)) for k, nm in enumerate(names_m)})

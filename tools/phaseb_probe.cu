@@ -10,7 +10,9 @@ __device__ __forceinline__ double inf_d() { return __longlong_as_double(0x7ff000
 // MODE 1: a preloaded (no per-j DADD for a): c table already holds s + c
 // MODE 2: no smem loads in the loop at all (p, a synthesized from registers)
 // MODE 3: like 0 but rows outer / levels inner
-// MODE 4: like 0 but compare against a copy (no loop-carried dependence on best): pure throughput of the mix
+// MODE 5: production form: (min, argmin) tracked per candidate (DADD, DSETP, 2 FSEL, SEL)
+// MODE 6: pair tournament: min of two successive candidates first, then against the running best; the argmin is
+//         tracked per pair and the winner inside the pair is recovered at the end by re-evaluation
 template <int TB, int TL, int MODE>
 __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const double *__restrict__ crow,
                                         const double *__restrict__ srow, double *__restrict__ pv, int jb, int je,
@@ -19,10 +21,11 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
     constexpr int TBP = (TB + 1) & ~1;
     const double inf = inf_d();
     double best[TB][TL];
+    int arg[TB][TL];
 #pragma unroll
     for (int a = 0; a < TB; ++a)
 #pragma unroll
-        for (int q = 0; q < TL; ++q) best[a][q] = inf;
+        for (int q = 0; q < TL; ++q) { best[a][q] = inf; arg[a][q] = -1; }
     double s[TL];
 #pragma unroll
     for (int q = 0; q < TL; ++q) s[q] = srow[q];
@@ -61,6 +64,38 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
                     const double v = __dadd_rn(a[q], p[r]);
                     if (best[r][q] > v) best[r][q] = v;
                 }
+        } else if (MODE == 5) {
+#pragma unroll
+            for (int q = 0; q < TL; ++q)
+#pragma unroll
+                for (int r = 0; r < TB; ++r) {
+                    const double v = __dadd_rn(a[q], p[r]);
+                    if (best[r][q] > v) { best[r][q] = v; arg[r][q] = j; }
+                }
+        } else if (MODE == 6) {
+            // second candidate of the pair
+            double p2[TBP], a2[TL];
+            const int j2 = (j + 1 < je) ? j + 1 : j;
+#pragma unroll
+            for (int k = 0; k < TBP / 2; ++k) {
+                const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)j2 * RP + 2 * k);
+                p2[2 * k] = x.x; p2[2 * k + 1] = x.y;
+            }
+#pragma unroll
+            for (int k = 0; k < TL / 2; ++k) {
+                const double2 x = *reinterpret_cast<const double2 *>(crow + (size_t)j2 * Kp + 2 * k);
+                a2[2 * k] = __dadd_rn(s[2 * k], x.x); a2[2 * k + 1] = __dadd_rn(s[2 * k + 1], x.y);
+            }
+#pragma unroll
+            for (int q = 0; q < TL; ++q)
+#pragma unroll
+                for (int r = 0; r < TB; ++r) {
+                    const double v0 = __dadd_rn(a[q], p[r]);
+                    const double v1 = __dadd_rn(a2[q], p2[r]);
+                    const double m = (v0 > v1) ? v1 : v0;           // ties: the earlier candidate
+                    if (best[r][q] > m) { best[r][q] = m; arg[r][q] = j; }
+                }
+            ++j;
         } else {
 #pragma unroll
             for (int q = 0; q < TL; ++q) {
@@ -75,6 +110,23 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
             }
         }
     }
+    if (MODE == 6) {
+        // recover the winner inside the winning pair
+#pragma unroll
+        for (int q = 0; q < TL; ++q)
+#pragma unroll
+            for (int r = 0; r < TB; ++r) {
+                const int j0 = arg[r][q] < 0 ? jb : arg[r][q];
+                const double v0 = __dadd_rn(__dadd_rn(s[q], crow[(size_t)j0 * Kp + q]), Prow[(size_t)j0 * RP + r]);
+                if (!(v0 == best[r][q]) && arg[r][q] >= 0) arg[r][q] = j0 + 1;
+            }
+    }
+    if (MODE >= 5) {
+#pragma unroll
+        for (int r = 0; r < TB; ++r)
+#pragma unroll
+            for (int q = 0; q < TL; ++q) pv[(size_t)r * Kp + q] += (double)arg[r][q];
+    }
 #pragma unroll
     for (int r = 0; r < TB; ++r)
 #pragma unroll
@@ -82,7 +134,7 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
 }
 
 template <int TB, int TL, int MODE>
-__global__ void __launch_bounds__(576, 1) k(double *out, long long *cyc, int K, int JS, int reps)
+__global__ void __launch_bounds__(TB * TL > 16 ? 256 : 512, 1) k(double *out, long long *cyc, int K, int JS, int reps)
 {
     extern __shared__ double sm[];
     constexpr int TBP = (TB + 1) & ~1;
@@ -117,7 +169,7 @@ void run(const char *name, int JS)
     constexpr int TBP = (TB + 1) & ~1;
     const int nLG = Kp / TL, tpg = ((nLG + 31) / 32) * 32;
     const int threads = JS * tpg;
-    if (threads > 576) return;
+    if (threads > (TB * TL > 16 ? 256 : 512)) return;
     size_t smem = (size_t)(Kp * TBP + K * Kp + Kp + JS * TB * Kp) * sizeof(double);
     double *d_out; long long *d_cyc;
     cudaMalloc(&d_out, 8); cudaMalloc(&d_cyc, 8);
@@ -135,19 +187,20 @@ void run(const char *name, int JS)
 
 int main()
 {
-    for (int JS : {4, 8}) {
-        run<7, 4, 0>("0 kernel form", JS);
-        run<7, 4, 1>("1 a preloaded", JS);
-        run<7, 4, 2>("2 no smem loads", JS);
-        run<7, 4, 3>("3 rows outer (interleaved)", JS);
+    for (int JS : {4, 7, 8}) {
+        run<7, 2, 0>("0 value only", JS);
+        run<7, 2, 5>("5 min+argmin (production)", JS);
+        run<7, 2, 6>("6 pair tournament", JS);
+    }
+    for (int JS : {4, 7, 8}) {
+        run<7, 4, 5>("5 min+argmin (production)", JS);
+        run<7, 4, 6>("6 pair tournament", JS);
     }
     for (int JS : {4, 8}) {
-        run<7, 2, 0>("0 kernel form", JS);
-        run<7, 2, 1>("1 a preloaded", JS);
-        run<7, 2, 2>("2 no smem loads", JS);
-        run<4, 4, 0>("0 kernel form", JS);
-        run<4, 2, 0>("0 kernel form", JS);
-        run<8, 1, 0>("0 kernel form 8x1 (TL odd n/a)", JS);
+        run<4, 4, 5>("5 min+argmin (production)", JS);
+        run<4, 4, 6>("6 pair tournament", JS);
+        run<8, 2, 5>("5 min+argmin (production)", JS);
+        run<8, 2, 6>("6 pair tournament", JS);
     }
     return 0;
 }
