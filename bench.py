@@ -266,8 +266,16 @@ def run_ours(args):
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # DRAM traffic of that kernel per launch: measured once per round with ncu on this very command at full size
+        # and committed under profiles/ (bench.py itself never runs under a profiler); scaled by n for other sizes
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "wavefront_traffic_r01.json")))
+            traffic = tr["dram_bytes_total"] * (inst.n - 1) / (100_000 - 1)
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_dadd / 1e12, "unit": "TFLOP/s",
-                    "frac": achieved / (peak_dadd / 1e12), "traffic": None,
+                    "frac": achieved / (peak_dadd / 1e12), "traffic": traffic,
                     "kernel": "bb200::wavefront_kernel", "kernel_ms": kms,
                     "flops_per_unit": 2, "units_per_launch": n_upd,
                     "peak_source": "live DADD issue-rate microbenchmark (bb200_fp64_peak mode 0) on this GPU; "

@@ -307,3 +307,52 @@ def test_full_size_properties(gpu_lib, oracle):
     np.testing.assert_array_equal(u2, u3)
     for p_ in (plan, plan2, plan3):
         p_.close()
+
+
+def test_uint16_argmin_and_large_level_sets(gpu_lib, oracle):
+    """K > 255 needs the uint16 argmin table; its jump-cost table does not fit in shared memory, so the plan
+    falls back to the per-stage kernels on its own (still CUDA, still bit-exact)."""
+    nu = [[0, 1, 2, 3, 4, 5, 6]] * 3                       # K = 343
+    it = oracle.product_iterator(nu)
+    rng = np.random.default_rng(12)
+    n, B = 6, 40
+    lv = oracle.level_values(nu, it)
+    u_old = lv[rng.integers(0, len(it), size=n)].astype(np.float64)
+    df = np.round(rng.standard_normal((n, 3)) * 4) / 4
+    plan = gpu_lib.TRMPlan(nu, it, n, B, 0.25, 1, 0.5)
+    plan.bellman(df, u_old)
+    st = plan.stats()
+    assert int(st["arg_bytes"]) == 2 and int(st["path"]) == 0
+    U, Phi, n_upd = oracle_tables(oracle, nu, it, n, B, df, u_old, 0.25, 1, 0.5, plan.cost)
+    np.testing.assert_array_equal(plan.export_phi(), Phi)
+    np.testing.assert_array_equal(plan.export_argmin(1, n, fill=0), U)
+    for Bn in (40, 13, 0):
+        u, ur = np.zeros((n, 3)), np.zeros((n, 3))
+        plan.eval_u(u, Bn)
+        oracle.eval_u_TRM(ur, u_old, U, Phi, Bn, nu)
+        np.testing.assert_array_equal(u, ur)
+    plan.close()
+
+
+def test_resident_interface_multiple_slots_one_launch(gpu_lib, oracle):
+    """bench.py's path: inputs uploaded once, several subproblems walked by ONE persistent launch."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    insts = [wl.synthetic(n=90, B=149, seed=100 + s, levels=4, M=3, tie_heavy=(s == 1)) for s in range(3)]
+    base = insts[0]
+    plan = gpu_lib.TRMPlan(base.nu, base.iterator, 90, 149, 0.25, 1, base.dt, batch=3)
+    for s, inst in enumerate(insts):
+        plan.upload(s, inst.df, inst.u_old)
+    launches0 = plan.stats()["launches"]
+    plan.bellman_resident(0, 3)
+    plan.sync()
+    assert plan.stats()["launches"] - launches0 == 4          # 3 prep kernels + one wavefront kernel
+    for s, inst in enumerate(insts):
+        U, Phi, n_upd = oracle_tables(oracle, inst.nu, inst.iterator, 90, 149, inst.df, inst.u_old, 0.25, 1, inst.dt, plan.cost)
+        np.testing.assert_array_equal(plan.export_phi(s), Phi)
+        assert plan.count_updates(s) == n_upd
+        plan.backtrack_resident(s, 100)
+        u, ur = np.zeros((90, 3)), np.zeros((90, 3))
+        plan.download(s, u)
+        oracle.eval_u_TRM(ur, inst.u_old, U, Phi, 100, inst.nu)
+        np.testing.assert_array_equal(u, ur)
+    plan.close()
