@@ -48,6 +48,7 @@ extern "C" {
 /* plan flags */
 #define BB200_FLAG_STAGE_KERNELS 1u /* force the one-launch-per-stage kernels (validation path)    */
 #define BB200_FLAG_NO_GRAPH 2u      /* do not capture TR iterations into a CUDA graph              */
+#define BB200_FLAG_FORCE_WAVEFRONT 4u /* never use the single-CTA small-problem kernel (tests)       */
 
 typedef struct bb200_plan bb200_plan;
 
@@ -159,7 +160,8 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *   0 last DP device time [ms] (CUDA events on the launching stream, all slots of the launch)
  *   1 last selection+backtrack device time [ms]
  *   2 kernels launched by this plan so far
- *   3 kernel path of the last DP: 0 = per-stage kernels, 1 = persistent wavefront kernel
+ *   3 kernel path of the last DP: 0 = per-stage kernels, 1 = persistent wavefront kernel,
+ *     2 = single-CTA small-problem kernel (value rows in shared memory, one CTA per subproblem)
  *   4 CTAs used by the last DP launch          5 source rows per CTA
  *   6 argmin bytes per cell (1 or 2)           7 device bytes owned by the plan
  *   8 threads per CTA of the last DP launch    9 j-split of the last DP launch

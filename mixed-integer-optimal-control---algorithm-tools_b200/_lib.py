@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BELLMAN_B200_LIB", os.path.join(HERE, "libbellman_b200.so"))
 
 OK, ERR_ARG, ERR_CUDA, ERR_INEXACT, ERR_STALE, ERR_STATE, ERR_NOMEM = range(7)
-FLAG_STAGE_KERNELS, FLAG_NO_GRAPH = 1, 2
+FLAG_STAGE_KERNELS, FLAG_NO_GRAPH, FLAG_FORCE_WAVEFRONT = 1, 2, 4
 
 c_plan_p = ctypes.c_void_p
 _F64P = ctypes.POINTER(ctypes.c_double)

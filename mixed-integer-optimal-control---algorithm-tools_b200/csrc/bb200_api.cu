@@ -69,6 +69,7 @@ struct bb200_plan {
     // device
     double *d_lvd = nullptr, *d_cost = nullptr, *d_halo = nullptr, *d_scalar = nullptr;
     long long *d_goff = nullptr;
+    size_t halo_elems = 0;
     unsigned long long *d_flags = nullptr;
     int *d_err = nullptr, *d_btmax = nullptr;
     long long *d_prof = nullptr;
@@ -90,7 +91,7 @@ struct bb200_plan {
     // geometry
     int num_sms = 0;
     size_t smem_max = 0;
-    bool wave_ok = false;
+    bool wave_ok = false, mini_ok = false;
     WaveCfg cfg{};
     int tune_ctas = 0, tune_js = 0, tune_variant = 0;
     // stats
@@ -119,9 +120,30 @@ int dev_alloc(bb200_plan *p, T **ptr, size_t count)
 int reconfigure(bb200_plan *p)
 {
     p->wave_ok = false;
+    p->mini_ok = false;
     if (p->flags & BB200_FLAG_STAGE_KERNELS) return BB200_OK;
+    // small stages: one CTA per subproblem, rows in shared memory (unless a wavefront geometry was requested)
+    if (!(p->tune_ctas || p->tune_js || p->tune_variant) && !(p->flags & BB200_FLAG_FORCE_WAVEFRONT) &&
+        mini_applicable(p->tab, p->smem_max)) {
+        p->mini_ok = true;
+        return BB200_OK;
+    }
     WaveCfg c{};
     if (wave_configure(p->tab, p->argw, p->num_sms, p->smem_max, p->tune_ctas, p->tune_js, p->tune_variant, c)) {
+        // the halo ring holds kHaloRing stages of value rows [B1][Kp], row-major like the rows in shared memory
+        const size_t need = (size_t)kHaloRing * p->B1 * p->Kp;
+        if (need > p->halo_elems) {
+            cudaStreamSynchronize(p->stream);
+            if (p->d_halo) { cudaFree(p->d_halo); p->dev_bytes -= p->halo_elems * sizeof(double); }
+            p->d_halo = nullptr;
+            p->halo_elems = 0;
+            if (cudaMalloc((void **)&p->d_halo, need * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(BB200_ERR_NOMEM, "cudaMalloc of the halo ring (%zu bytes) failed", need * sizeof(double));
+            }
+            p->halo_elems = need;
+            p->dev_bytes += need * sizeof(double);
+        }
         p->cfg = c;
         p->wave_ok = true;
     }
@@ -167,7 +189,13 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false)
         p->launches += 1;
         p->slots[s].has_dp = true;
     }
-    if (p->wave_ok) {
+    if (p->mini_ok) {
+        if (!capturing) CU(cudaEventRecord(p->ev[4], st));
+        CU(launch_mini(p->tab, p->d_slots + slot0, count, p->argw, st));
+        if (!capturing) CU(cudaEventRecord(p->ev[5], st));
+        p->launches += 1;
+        p->last_path = 2;
+    } else if (p->wave_ok) {
         CU(cudaMemsetAsync(p->d_flags, 0, (size_t)p->cfg.G * kFlagStride * sizeof(unsigned long long), st));
         WaveCfg c = p->cfg;
         c.nsub = count;
@@ -270,7 +298,7 @@ int sync_and_check(bb200_plan *p)
     if (p->dp_timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->last_dp_ms = ms;
-        if (p->last_path == 1 && cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]) == cudaSuccess) p->last_wave_ms = ms;
+        if (p->last_path >= 1 && cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]) == cudaSuccess) p->last_wave_ms = ms;
         p->dp_timed = false;
     }
     if (p->bt_timed) {
@@ -363,7 +391,6 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
     if ((rc = dev_alloc(p, &p->d_btmax, 1))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_scalar, 8))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_flags, (size_t)prop.multiProcessorCount * kFlagStride))) return bail(rc);
-    if ((rc = dev_alloc(p, &p->d_halo, (size_t)kHaloRing * p->B1 * p->Kp))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_slots, (size_t)batch))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_prof, (size_t)prop.multiProcessorCount * 16))) return bail(rc);
 #define CUB(call)                                                                                   \
@@ -411,7 +438,7 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
     CUB(cudaMallocHost((void **)&p->h_rec, 4 * kMaxRadii * sizeof(double)));
     CUB(cudaMallocHost((void **)&p->h_err, 4 * sizeof(int)));
 #undef CUB
-    reconfigure(p);
+    if ((rc = reconfigure(p))) return bail(rc);
     *out = p;
     return BB200_OK;
 }
@@ -437,8 +464,10 @@ int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t vari
     if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
     Guard g(plan);
     plan->tune_ctas = ctas; plan->tune_js = jsplit; plan->tune_variant = variant;
-    reconfigure(plan);
-    if (!plan->wave_ok && !(plan->flags & BB200_FLAG_STAGE_KERNELS) && (ctas || jsplit || variant))
+    if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }  // geometry is baked in
+    int rc = reconfigure(plan);
+    if (rc) return rc;
+    if (!plan->wave_ok && !plan->mini_ok && !(plan->flags & BB200_FLAG_STAGE_KERNELS) && (ctas || jsplit || variant))
         return fail(BB200_ERR_ARG, "requested tuning (ctas=%d, jsplit=%d, variant=%d) is not launchable", ctas, jsplit, variant);
     return BB200_OK;
 }
@@ -556,8 +585,9 @@ int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, plan->ev[0], plan->ev[1]) == cudaSuccess) plan->last_dp_ms = ms;
         plan->slots[0].has_dp = true;
-        plan->launches += 4 + (plan->wave_ok ? 0 : (double)plan->n - 1);  // prep, DP, selection, backtrack
-        plan->last_path = plan->wave_ok ? 1 : 0;
+        const bool one_launch = plan->wave_ok || plan->mini_ok;
+        plan->launches += 4 + (one_launch ? 0 : (double)plan->n - 1);  // prep, DP, selection, backtrack
+        plan->last_path = plan->mini_ok ? 2 : (plan->wave_ok ? 1 : 0);
         plan->graph_replays += 1;
         std::memcpy(u_out, plan->h_u, io);
         if (phi_star) *phi_star = plan->h_rec[0];

@@ -20,7 +20,8 @@ namespace bb200 {
 
 constexpr int kChunk = 64;        // stages per TMA chunk of df / u_old
 constexpr int kWaveThreadsBig = 256;    // wavefront CTA cap for large register tiles (7 compute warps + comm): 255 regs/thread
-constexpr int kWaveThreadsSmall = 512;  // cap for small tiles (15 compute warps + comm): 128 regs/thread
+constexpr int kWaveThreadsMid = 384;    // small tiles with up to 12 warps: 168 regs/thread (room for a good phase-B schedule)
+constexpr int kWaveThreadsSmall = 512;  // cap for small tiles (up to 16 warps): 128 regs/thread
 constexpr int kMaxM = 8;          // controls supported by the kernels
 constexpr int kFlagStride = 16;   // u64 words between per-CTA progress flags (128 B apart)
 constexpr int kHaloRing = 8;      // stages of halo kept in flight between neighbouring CTAs
@@ -113,6 +114,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     }
+}
+// Non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 // 1-D bulk TMA global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)

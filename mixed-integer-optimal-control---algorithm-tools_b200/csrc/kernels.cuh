@@ -7,6 +7,8 @@ namespace bb200 {
 // kernels_common.cu
 void launch_prep(const Tables &t, const SlotDev &slot, int *err, int *btmax, cudaStream_t st);
 int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream_t st);
+bool mini_applicable(const Tables &t, size_t smem_max);
+cudaError_t launch_mini(const Tables &t, const SlotDev *d_slots, int count, int argw, cudaStream_t st);
 void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bnew_ptr, int *err, cudaStream_t st);
 void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st);
 void launch_pred_integral(const Tables &t, const SlotDev &slot, double *out, cudaStream_t st);
@@ -24,6 +26,7 @@ struct WaveCfg {
     int jper;     // successors per group = ceil(K / JS)
     int tpg;      // threads per group (multiple of 32)
     int RP;       // padded row positions per level in the shared value rows
+    int pub;      // 1: a separate publisher warp moves the progress counter (stages too short to hide the fence)
     int threads;  // JS * tpg
     size_t smem;  // dynamic shared memory bytes
     int nsub;     // subproblems walked by this launch

@@ -102,6 +102,143 @@ __global__ void stage_kernel(Tables t, SlotDev slot, int i /* 1-based stage */)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small-problem path: one CTA walks all stages of one subproblem with both value rows in shared memory
+// (the reference's rolling 2-slot Phi, HelpFunctions.jl:27,47,71) and one __syncthreads per stage.  Used when a
+// stage is too little work to spread over the GPU (K = 3..5 example shapes: ~1.5e3 candidates per stage), where
+// any inter-CTA hand-over would cost more than the stage itself.  blockIdx.x = subproblem slot, so a batch of
+// small subproblems runs on as many SMs concurrently.  Same arithmetic as stage_kernel (thread = source cell,
+// straight scan in iterator order); the stage's level costs arrive in 32-stage chunks by 1-D bulk TMA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMiniChunk = 32;
+
+template <typename ArgT>
+__global__ void __launch_bounds__(1024, 1) mini_kernel(Tables t, const SlotDev *slots)
+{
+    constexpr ArgT MARK = (ArgT)~(ArgT)0;
+    extern __shared__ __align__(128) unsigned char smem_mini[];
+    const SlotDev slot = slots[blockIdx.x];
+    const int K = t.K, Kp = t.Kp, B1 = t.B1, n = t.n;
+    const int cells = B1 * K;
+    // layout: mbar[2] | ss[2][chunk][Kp] | bt[2][chunk][Kp] | cost[K][K] | P[2][B1][K]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_mini);
+    double *ssb = reinterpret_cast<double *>(smem_mini + 128);
+    int *btb = reinterpret_cast<int *>(ssb + 2 * kMiniChunk * Kp);
+    double *cs = reinterpret_cast<double *>(btb + 2 * kMiniChunk * Kp);
+    double *P = cs + (size_t)K * K;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const double inf = d_inf();
+    ArgT *arg = reinterpret_cast<ArgT *>(slot.arg);
+    for (int x = tid; x < K * K; x += NT) cs[x] = t.cost[(x / K) * Kp + (x % K)];
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // chunk c holds stage rows [c*chunk, (c+1)*chunk); rows are consumed downwards from n-1
+    auto load_chunk = [&](int c) {
+        const int b = c & 1;
+        const int row0 = c * kMiniChunk;
+        const int rows = min(kMiniChunk, n - row0);
+        mbar_expect_tx(&mbar[b], (uint32_t)(rows * Kp * (sizeof(double) + sizeof(int))));
+        tma_load_1d(ssb + (size_t)b * kMiniChunk * Kp, slot.ss_all + (size_t)row0 * Kp, (uint32_t)(rows * Kp * sizeof(double)), &mbar[b]);
+        tma_load_1d(btb + (size_t)b * kMiniChunk * Kp, slot.bt_all + (size_t)row0 * Kp, (uint32_t)(rows * Kp * sizeof(int)), &mbar[b]);
+    };
+    int chunk_cur = (n - 1) / kMiniChunk;
+    uint32_t phase_bits = 0;
+    if (tid == 0) {
+        load_chunk(chunk_cur);
+        if (chunk_cur >= 1) load_chunk(chunk_cur - 1);
+    }
+    mbar_wait(&mbar[chunk_cur & 1], (phase_bits >> (chunk_cur & 1)) & 1u);
+    phase_bits ^= 1u << (chunk_cur & 1);
+    // terminal stage n (HelpFunctions.jl:27-43) into the slot of stage n
+    {
+        const double *sn = ssb + ((size_t)(chunk_cur & 1) * kMiniChunk + ((n - 1) % kMiniChunk)) * Kp;
+        const int *bn = btb + ((size_t)(chunk_cur & 1) * kMiniChunk + ((n - 1) % kMiniChunk)) * Kp;
+        double *Pt = P + (size_t)((n + 1) & 1) * cells;
+        for (int x = tid; x < cells; x += NT) {
+            const int b = x / K, l = x - b * K;
+            Pt[x] = (b == bn[l]) ? sn[l] : inf;
+        }
+    }
+    __syncthreads();
+    for (int i = n - 1; i >= 1; --i) {
+        const int ri = i - 1, ch = ri / kMiniChunk;
+        if (ch != chunk_cur) {
+            // every thread finished reading chunk ch+1 before the barrier that ended the previous stage
+            chunk_cur = ch;
+            if (tid == 0 && ch >= 1) load_chunk(ch - 1);
+            mbar_wait(&mbar[ch & 1], (phase_bits >> (ch & 1)) & 1u);
+            phase_bits ^= 1u << (ch & 1);
+        }
+        const double *ss = ssb + ((size_t)(ch & 1) * kMiniChunk + (ri % kMiniChunk)) * Kp;
+        const int *bt = btb + ((size_t)(ch & 1) * kMiniChunk + (ri % kMiniChunk)) * Kp;
+        double *Pc = P + (size_t)((i + 1) & 1) * cells;       // slot(i)   written
+        const double *Pn = P + (size_t)(i & 1) * cells;       // slot(i+1) read
+        for (int x = tid; x < cells; x += NT) {
+            const int bsrc = x / K, l = x - bsrc * K;
+            const int b = bt[l];
+            if (bsrc < b) Pc[x] = inf;                        // target rows nobody reaches (:47)
+            const int tgt = bsrc + b;
+            if (tgt >= B1) continue;                          // outside `for b = 0:B-b~` (:69)
+            const double s = ss[l];
+            const double *pn = Pn + (size_t)bsrc * K;
+            double best = inf;
+            int a = (int)MARK;
+            for (int j = 0; j < K; ++j) {
+                const double v = __dadd_rn(__dadd_rn(s, cs[j * K + l]), pn[j]);  // :67, :71
+                if (best > v) { best = v; a = j; }                                // :73-76
+            }
+            Pc[(size_t)tgt * K + l] = best;
+            arg[((size_t)(i - 1) * B1 + bsrc) * Kp + l] = (ArgT)a;
+        }
+        __syncthreads();
+    }
+    // exit state (S7): stage-1 values in slot 0, stage-2 values in slot 1 (the prep kernel pre-filled +Inf)
+    for (int sl = 0; sl < 2; ++sl) {
+        if (n == 1 && sl == 1) break;
+        const double *Ps = P + (size_t)sl * cells;
+        for (int x = tid; x < cells; x += NT) {
+            const int b = x / K, l = x - b * K;
+            slot.phi[((size_t)sl * B1 + b) * Kp + l] = Ps[x];
+        }
+    }
+}
+
+size_t mini_smem_bytes(const Tables &t)
+{
+    return 128 + (size_t)2 * kMiniChunk * t.Kp * (sizeof(double) + sizeof(int)) + (size_t)t.K * t.K * sizeof(double) +
+           (size_t)2 * t.B1 * t.K * sizeof(double) + 64;
+}
+
+// The small-problem kernel is chosen when a stage has little work and everything fits in shared memory.
+bool mini_applicable(const Tables &t, size_t smem_max)
+{
+    const double relax_per_stage = (double)t.B1 * t.K * t.K;
+    return relax_per_stage <= 60000. && mini_smem_bytes(t) <= smem_max;
+}
+
+cudaError_t launch_mini(const Tables &t, const SlotDev *d_slots, int count, int argw, cudaStream_t st)
+{
+    const size_t smem = mini_smem_bytes(t);
+    int threads = ((t.B1 * t.K + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
+    if (threads < 64) threads = 64;
+    cudaError_t e;
+    if (argw == 1) {
+        e = cudaFuncSetAttribute(mini_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mini_kernel<uint8_t><<<count, threads, smem, st>>>(t, d_slots);
+    } else {
+        e = cudaFuncSetAttribute(mini_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mini_kernel<uint16_t><<<count, threads, smem, st>>>(t, d_slots);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Selection (HelpFunctions.jl:102-112): argmin over phi[0][0..Bnew][*] in the reference's column-major
 // order (budget fastest, then grid offset) with Julia 1.10 findmin semantics (S8).  One CTA; per-thread
 // scan, warp-shuffle reduction, then across warps through shared memory.

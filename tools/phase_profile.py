@@ -8,8 +8,9 @@ import mioc_b200 as m
 wl = importlib.import_module(m.__name__ + ".workloads")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 tune = [int(x) for x in sys.argv[2:5]] if len(sys.argv) > 4 else [0, 0, 0]
-inst = wl.synthetic(n=n, B=999, seed=20251018)
-plan = m.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt)
+kind = sys.argv[5] if len(sys.argv) > 5 else "synthetic"
+inst = wl.synthetic(n=n, B=999, seed=20251018) if kind == "synthetic" else wl.example_shaped(kind, n=n, seed=3)
+plan = m.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt, flags=4)
 plan.tune(*tune)
 plan.upload(0, inst.df, inst.u_old)
 plan.bellman_resident(0, 1); plan.sync()
@@ -18,15 +19,16 @@ plan.bellman_resident(0, 1); plan.sync()
 st = plan.stats()
 prof = plan.profile(True, fetch=True)
 G = int(st["ctas"])
-print(f"ctas={G} rows={int(st['rows_per_cta'])} threads={int(st['threads'])} js={int(st['jsplit'])} wave_ms={st['wave_ms']:.3f} "
+print(f"{kind} n={n} K={inst.K} B={inst.B} variant={int(st.get('variant', -1))} ctas={G} rows={int(st['rows_per_cta'])} threads={int(st['threads'])} js={int(st['jsplit'])} wave_ms={st['wave_ms']:.3f} "
       f"us/stage={st['wave_ms']*1e3/(n-1):.2f}  T upd/s={plan.count_updates()/st['wave_ms']/1e9:.3f}")
 names_c = ["wait_full", "phaseB", "barrier", "phaseC"]
-names_m = ["eval", "flagwait", "gather", "donewait", "publish"]
+names_m = ["eval", "flagwait", "merge", "donewait", "publish"]
 for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
     row = prof[gsel]
     stg = max(row[4], 1)
     print(f"cta {gsel:3d} compute cyc/stage: " + "  ".join(f"{nm}={row[k]/stg:8.0f}" for k, nm in enumerate(names_c)) +
           f" | comm: " + "  ".join(f"{nm}={row[8+k]/max(row[13],1):8.0f}" for k, nm in enumerate(names_m)))
 avg = prof[:G].mean(axis=0)
-print("warp1 (other scheduler) cyc/stage: phaseB=%d barrier=%d phaseC=%d" % tuple(round(avg[k]/max(avg[4],1)) for k in (5,6,7)))
+print("phase C split cyc/stage: halo wait=%d combine=%d scatter=%d" % tuple(round(avg[k]/max(avg[4],1)) for k in (5,6,7)))
+print("comm halo TMA wait cyc/stage:", round(avg[14]/max(avg[13],1)))
 print("avg compute:", {nm: round(avg[k]/max(avg[4],1)) for k, nm in enumerate(names_c)}, "comm:", {nm: round(avg[8+k]/max(avg[13],1)) for k, nm in enumerate(names_m)})
