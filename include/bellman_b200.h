@@ -167,6 +167,8 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *   8 threads per CTA of the last DP launch    9 j-split of the last DP launch
  *  10 device time [ms] of the last persistent wavefront kernel alone (events around that launch)
  *  11 number of CUDA-graph replays performed by bb200_solve
+ *  12 tile variant of the wavefront kernel (1-based, as accepted by bb200_plan_tune)
+ *  13 scatter warps per CTA of the wavefront kernel
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);
 
@@ -177,12 +179,13 @@ int bb200_fp64_peak(int device, int32_t mode, double target_ms, double *ops_per_
 
 /* In-kernel cycle profile of the wavefront kernel.  enable != 0 switches the counters on for later launches;
  * if out != NULL the counters of the last launch are copied out, 16 int64 per CTA for min(max_ctas, SMs) CTAs:
- *   [0..4]  compute warp 0: cycles waiting for rows, in phase B, at the CTA barrier, in phase C; stages
- *   [8..13] comm warp: cycles in stage-cost evaluation, neighbour waits, halo gather, waiting for compute,
- *           publishing progress; stages */
+ *   [0..4]  compute warp 0: cycles waiting for finished rows / cost rows, in phase B, handing over; [3] unused; stages
+ *   [5..7]  scatter warp 0: cycles waiting for the scan, waiting for halo rows / ring space, in phase C
+ *   [8..13] comm warp: event-loop trips, idle trips, predecessor polls, successor polls, unused, cost rows loaded */
 int bb200_profile(bb200_plan *plan, int32_t enable, int64_t *out, int32_t max_ctas);
 
-/* Tuning knobs for experiments (0 = automatic): number of CTAs, j-split, rows per thread. */
+/* Tuning knobs for experiments (0 = automatic): number of CTAs, j-split, tile variant (1-based index into the
+ * wavefront kernel's tile table; add 100 * NS to force NS scatter warps per CTA). */
 int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t variant);
 
 #ifdef __cplusplus

@@ -158,10 +158,10 @@ class TRMPlan:
         return v.value
 
     def stats(self):
-        out = np.zeros(12, dtype=np.float64)
-        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 12))
+        out = np.zeros(14, dtype=np.float64)
+        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 14))
         keys = ("dp_ms", "backtrack_ms", "launches", "path", "ctas", "rows_per_cta", "arg_bytes",
-                "device_bytes", "threads", "jsplit", "wave_ms", "graph_replays")
+                "device_bytes", "threads", "jsplit", "wave_ms", "graph_replays", "variant", "scatter_warps")
         return dict(zip(keys, out.tolist()))
 
     def profile(self, enable=True, fetch=False, max_ctas=148):

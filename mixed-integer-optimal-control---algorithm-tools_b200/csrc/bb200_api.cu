@@ -802,12 +802,13 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
 {
     if (!plan || !out) return fail(BB200_ERR_ARG, "bad arguments");
     Guard g(plan);
-    const double v[12] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+    const double v[14] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
                           plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
                           (double)plan->argw, (double)plan->dev_bytes,
                           plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.,
-                          plan->last_wave_ms, plan->graph_replays};
-    for (int k = 0; k < count && k < 12; ++k) out[k] = v[k];
+                          plan->last_wave_ms, plan->graph_replays,
+                          plan->wave_ok ? (double)(plan->cfg.variant + 1) : 0., plan->wave_ok ? (double)plan->cfg.NS : 0.};
+    for (int k = 0; k < count && k < 14; ++k) out[k] = v[k];
     return BB200_OK;
 }
 

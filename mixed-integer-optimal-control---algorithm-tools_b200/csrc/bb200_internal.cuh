@@ -24,7 +24,7 @@ constexpr int kWaveThreadsMid = 384;    // small tiles with up to 12 warps: 168 
 constexpr int kWaveThreadsSmall = 512;  // cap for small tiles (up to 16 warps): 128 regs/thread
 constexpr int kMaxM = 8;          // controls supported by the kernels
 constexpr int kFlagStride = 16;   // u64 words between per-CTA progress flags (128 B apart)
-constexpr int kHaloRing = 8;      // stages of halo kept in flight between neighbouring CTAs
+constexpr int kHaloRing = 32;     // stages of halo kept in flight between neighbouring CTAs (deep: a push can span many slices)
 
 struct SlotDev {
     const double *df;     // [nPad][M]

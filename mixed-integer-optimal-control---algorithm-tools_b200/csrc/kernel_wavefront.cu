@@ -3,31 +3,36 @@
 // One launch walks every stage i = n-1 .. 1 of bellman_TRM! (HelpFunctions.jl:45-82) for one or more
 // subproblems.  Work decomposition:
 //
-//   * The budget axis is cut into G slices of R consecutive SOURCE rows b' (one persistent CTA each,
-//     one CTA per SM).  A target cell (b, l) of stage i has exactly one source row b' = b - b~_l(i)
-//     (HelpFunctions.jl:69-71), so slicing by source row partitions the cells, every CTA reads only the
-//     value rows it owns (resident in shared memory) and PUSHES results whose target row b' + b~_l
-//     belongs to a higher slice into a global ring of value rows (row-major, the same layout as the rows in
-//     shared memory), so the consumer takes its R rows with ONE bulk TMA straight into the rows the next stage
-//     reads, and its own results simply overwrite the cells it produces itself.  Budget only flows upwards, therefore slice g depends on slices
-//     g-1 .. g-D only (D = ceil(max b~ / R)): the slices form a pipeline and low-budget CTAs run ahead in
-//     time.  Neighbours synchronise through per-CTA progress counters in global memory (release/acquire),
-//     never through a grid-wide barrier.
-//   * Warp specialisation inside a CTA.  COMPUTE warps do the arithmetic; one COMM warp runs one stage
-//     ahead: it brings the stage's level costs s_l(i) and budget uses b~_l(i) (evaluated from df[:, i] and
-//     u_old[:, i] by the prep kernel, S3) and the halo rows the predecessors pushed into shared memory by 1-D
-//     bulk TMA (cp.async.bulk + mbarrier), polls the neighbours' progress counters, merges the halo cells
-//     (and the +Inf of unreachable cells) into the next value rows, and publishes this CTA's own progress.  Compute and comm hand over through two shared-memory mbarriers
-//     (`full`: rows ready, `done`: stage finished), so no global-memory latency is exposed in steady state.
+//   * The budget axis is cut into G slices of R consecutive SOURCE rows b' (one persistent CTA each, one CTA per
+//     SM).  A target cell (b, l) of stage i has exactly one source row b' = b - b~_l(i) (HelpFunctions.jl:69-71),
+//     so slicing by source row partitions the cells: every CTA reads only the value rows it owns (resident in
+//     shared memory, row-major) and PUSHES results whose target row b' + b~_l belongs to a higher slice into a
+//     global ring of value rows with the same layout.  The consumer takes its R rows with ONE bulk TMA straight
+//     into the rows the next stage reads; its own results then overwrite the cells it produces itself.  Budget
+//     only flows upwards, so slice g depends on slices g-1 .. g-D only (D = ceil(max b~ / R)): the slices form a
+//     pipeline and low-budget CTAs run ahead in time.  Neighbours synchronise through per-CTA progress counters
+//     in global memory (release/acquire), never through a grid-wide barrier.
+//   * The same "budget only flows upwards" argument is used once more INSIDE a CTA: its rows are split into a
+//     lower sub-slice A and an upper sub-slice B.  The compute warps alternate scan(A, i), scan(B, i),
+//     scan(A, i-1), ...; SCATTER warps trail one sub-step behind and finish sub-slice A of stage i (combine the
+//     partial minima, store the argmin, scatter the values) while the compute warps already scan sub-slice B.
+//     scan(A, i-1) needs only finish(A, i) -- rows of A never receive values from B -- so the latency-bound
+//     finishing work is hidden behind the issue-bound scan instead of alternating with it.
+//   * Warp roles:  COMPUTE warps (phase B below);  SCATTER warps (phase C, the terminal stage);  one COMM warp
+//     (cost rows and halo rows by 1-D bulk TMA, neighbour counters, back-pressure on the ring);  one PUBLISHER
+//     warp (fence + progress counter).  Compute and scatter hand over through shared-memory mbarriers
+//     (`scanned[v]`, `finished[v]`), the comm and publisher warps follow monotone counters in shared memory, so
+//     no role ever blocks another one that could make progress.
 //   * Phase B (compute): the stage is a small min-plus matrix product C[b', l] = min_j (s_l + c_jl) + P[b', j].
 //     A thread owns a TB x TL register tile of cells, thread groups split the successor range j (JS groups).
 //     Every candidate is two separately rounded FP64 adds (:67, :71) and a strict '>' (:73) that keeps the
 //     earliest successor on ties and never lets +Inf/NaN win -- exactly the reference's arithmetic.  On sm_100a
 //     an FP64 instruction occupies two issue slots, so a candidate costs DADD(2)+DSETP(2)+2 FSEL+SEL = 7 slots
 //     (profiles/pipe_probe_r01.txt); the kernel is issue bound, not FP64-pipe or HBM bound.
-//   * Phase C (compute): the JS partial (min, argmin) pairs of a cell are combined in ascending-j order with the
-//     same strict '>' (the earliest group holding the minimum wins).  The value goes to the next stage's rows (own slice: shared memory; higher slice: global halo ring), the
-//     argmin to HBM once per cell as uint8/uint16 indexed by source row (coalesced rows).
+//   * Phase C (scatter): the JS partial (min, argmin) pairs of a cell are combined in ascending-j order with the
+//     same strict '>' (the earliest group holding the minimum wins).  The value goes to the next stage's rows
+//     (own slice: shared memory; higher slice: global ring), the argmin to HBM once per cell as uint8 indexed
+//     by source row (coalesced rows).
 #include "bb200_internal.cuh"
 #include "kernels.cuh"
 
@@ -40,56 +45,92 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void compute_barrier(int nthreads)
+// monotone counters in shared memory (CTA scope)
+__device__ __forceinline__ unsigned long long lds_acquire(const uint64_t *p)
 {
-    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    unsigned long long v;
+    asm volatile("ld.acquire.cta.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
 }
-
-// Spin until *flag >= want: relaxed polls, then ONE acquire load of the satisfied counter (an acquire load is far
-// cheaper than a full fence.acq_rel.gpu, which costs 1-3 thousand cycles on a busy SM).  A bounded watchdog turns a
-// lost dependency into an error code instead of a hung GPU: after ~2^23 polls the CTA raises the abort flag and
-// every poller gives up.
-__device__ __forceinline__ void wait_flag(const unsigned long long *flag, long long want, int *err)
+__device__ __forceinline__ void sts_release(uint64_t *p, unsigned long long v)
 {
-    if (want <= 0) return;
+    asm volatile("st.release.cta.shared::cta.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
+// 32-bit event counters: native shared-memory RED; compared wrap-safe (difference as signed)
+__device__ __forceinline__ void reds_release_inc(uint64_t *p)
+{
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(1u) : "memory");
+}
+__device__ __forceinline__ unsigned int lds_acquire_u32(const uint64_t *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+// has the counter reached `want` events?  (events are counted modulo 2^32; the lag is always far below 2^31)
+__device__ __forceinline__ bool reached(unsigned int cnt, unsigned long long want) { return (int)(cnt - (unsigned int)want) >= 0; }
+
+// mbarrier wait with a watchdog: a lost hand-over becomes an error code (err[2] watchdog, err[3] abort) instead of
+// a hung GPU.  Once the abort flag is up every wait gives up quickly so that the launch drains.
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int *err)
+{
+    if (mbar_test(bar, parity)) return;
     unsigned int spins = 0;
-    while ((long long)ld_relaxed(flag) < want) {
-        __nanosleep(100);  // the comm warp shares a scheduler with compute warps: do not burn their issue slots
+    long long t0 = 0;
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
         if ((++spins & 0x3ffu) == 0) {
-            if (*(volatile int *)&err[3]) return;
-            if (spins > (1u << 23)) {
-                atomicOr(&err[2], 1);
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (*(volatile int *)&err[3]) {
+                if (spins >= 4096u) return;
+            } else if (now - t0 > 6000000000LL) {  // ~3 s
+                atomicOr(&err[2], 2);
                 atomicOr(&err[3], 1);
                 return;
             }
         }
     }
-    (void)ld_acquire(flag);
 }
 
+constexpr long long kNever = (long long)1 << 62;
+
+// shared-memory synchronisation words
+enum {
+    MB_COST = 0,      // [0..2]  cost rows of global step T landed in buffer T % 3           (TMA, tx count)
+    MB_HALO = 3,      // [3..4]  halo rows pushed during stage i landed, barrier i & 1        (TMA, tx count)
+    MB_SCANNED = 5,   // [5..6]  compute warps finished phase B of sub-slice v                (one arrival per warp)
+    MB_FINISHED = 7,  // [7..8]  scatter warps finished phase C of sub-slice v                (one arrival per warp)
+    CNT_SCANNED = 9,  // counter: compute-warp arrivals after the LAST sub-slice of a stage
+    CNT_FINISHED = 10,  // counter: scatter-warp arrivals after the LAST sub-slice of a step (terminal stage included)
+    RING_OK = 11,     // counter: highest global step whose pushes may overwrite their ring slot
+    SYNC_WORDS = 16
+};
+
 struct Smem {
-    uint64_t *mbar;   // [0..2] cost rows landed (buffer i%3), [3] halo landed, [4] full, [5] done, [6] relay counter
-    double *ss;       // [3][Kp]   stage cost of stage i in ss[i%3]         (TMA destination)
-    int *bts;         // [3][Kp]   budget use of stage i in bts[i%3]        (TMA destination)
+    uint64_t *mbar;   // SYNC_WORDS synchronisation words, see the enum above
+    double *ss;       // [3][Kp]   stage cost of global step T in ss[T%3]        (TMA destination)
+    int *bts;         // [3][Kp]   budget use of global step T in bts[T%3]       (TMA destination)
     double *Ps;       // [2][R][Kp] value rows (row-major) read by stage i in Ps[i&1]  (halo rows: TMA destination)
     double *cs;       // [K*Kp]    jump costs
     double *pv;       // [JS*R*Kp] partial minima of the j-groups
     unsigned char *pa;  // ArgT[JS*R*Kp] partial argmins
+    int *umap;        // [R*Kp/32] phase-C work unit -> (row << 16) | first level
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -97,15 +138,16 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int argw, unsigned char *base, Smem *s)
 {
     size_t off = 0;
-    size_t o[7];
-    const size_t sizes[7] = {8 * sizeof(uint64_t),
+    size_t o[8];
+    const size_t sizes[8] = {SYNC_WORDS * sizeof(uint64_t),
                              3 * (size_t)t.Kp * sizeof(double),
                              3 * (size_t)t.Kp * sizeof(int),
                              2 * (size_t)t.Kp * c.R * sizeof(double),
                              (size_t)t.K * t.Kp * sizeof(double),
                              (size_t)c.JS * c.R * t.Kp * sizeof(double),
-                             (size_t)c.JS * c.R * t.Kp * (size_t)argw};
-    for (int k = 0; k < 7; ++k) {
+                             (size_t)c.JS * c.R * t.Kp * (size_t)argw,
+                             (size_t)c.R * (t.Kp / 32) * sizeof(int)};
+    for (int k = 0; k < 8; ++k) {
         o[k] = off;
         off = align_up(off + sizes[k], 128);
     }
@@ -117,6 +159,7 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
         s->cs = reinterpret_cast<double *>(base + o[4]);
         s->pv = reinterpret_cast<double *>(base + o[5]);
         s->pa = base + o[6];
+        s->umap = reinterpret_cast<int *>(base + o[7]);
     }
     return off;
 }
@@ -127,9 +170,6 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
 // Two successors per trip: P[r][j], P[r][j+1] are neighbours in the row-major value rows, so one 16-byte
 // warp-broadcast load serves both (jb is even by construction).
 // Cost per candidate and cell on sm_100a: DADD + DSETP (two issue slots each) + 2 FSEL + SEL = 7 slots.
-#ifndef BB_BVAR
-#define BB_BVAR 0
-#endif
 template <int TB, int TL, typename ArgT>
 __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const double *__restrict__ crow,
                                         const double *__restrict__ srow, double *__restrict__ pv,
@@ -148,17 +188,7 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
     for (int q = 0; q < TL; ++q) s[q] = srow[q];
     // main loop: full pairs, one straight-line block so that the two candidates' chains interleave
     const int je2 = jb + ((je - jb) & ~1);
-#if BB_BVAR == 1
-#pragma unroll 2
-#elif BB_BVAR == 3
-#pragma unroll 8
-#elif BB_BVAR == 4
-#pragma unroll 3
-#elif BB_BVAR == 5
-#pragma unroll 1
-#else
 #pragma unroll 4
-#endif
     for (int j = jb; j < je2; j += 2) {
         double p0[TB], p1[TB];
 #pragma unroll
@@ -223,221 +253,415 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
         }
 }
 
+// ===================================== SCATTER warps (phase C) ====================================
+struct FinishArgs {
+    const double *pv;
+    const unsigned char *pa;  // ArgT[]
+    const int *bt;            // budget use of this stage's levels
+    const int *umap;          // work unit -> (row << 16) | first level, see scatter_warp
+    double *Pn;               // rows of the next stage, [R][Kp]
+    double *hring;            // ring slot of this step at row r0, [B1 - r0][Kp]
+    double *phi;              // exit slot that receives this stage's values (i <= 2) at row r0, or nullptr
+    unsigned char *argrow;    // ArgT*: argmin table of this stage at source row r0
+    int JS, R, Kp, K, B1, r0;
+};
+
+// Finishes the cells of `CU` work units at once (a unit = 32 consecutive levels of one source row, one cell per
+// lane) so that the dependent load -> compare -> select chains of different cells overlap.  Units [ub, ue) of the
+// CTA belong to the sub-slice being finished; warp sw of NS takes every NS-th one.
+template <int JSC, typename ArgT>
+__device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue, int sw, int NS, int lane, long long *pcc)
+{
+    long long tq0 = pcc ? clock64() : 0;
+    constexpr int CU = 4;
+    constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
+    const double inf = d_inf();
+    const double *__restrict__ pv = a.pv;
+    const ArgT *__restrict__ pa = reinterpret_cast<const ArgT *>(a.pa);
+    const int *__restrict__ btp = a.bt;
+    const int *__restrict__ umap = a.umap;
+    ArgT *__restrict__ argrow = reinterpret_cast<ArgT *>(a.argrow);
+    double *__restrict__ Pn = a.Pn;
+    double *__restrict__ hring = a.hring;
+    const int RK = a.R * a.Kp;
+    const int rows_left = a.B1 - a.r0;  // rows of this slice that exist in the table
+    for (int u0 = ub + sw; u0 < ue; u0 += NS * CU) {
+        double val[CU];
+        int arg[CU], x_[CU], y_[CU];
+        bool no_src[CU], ok[CU];
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const int unit = u0 + u * NS;
+            const bool live = unit < ue;
+            const int m = umap[live ? unit : ub];
+            const int row = m >> 16, l = (m & 0xffff) + lane;
+            const int bt = btp[l];
+            const bool in_tab = live && l < a.K && row < rows_left;
+            x_[u] = row * a.Kp + l;
+            y_[u] = x_[u] + bt * a.Kp;  // (target row - r0) * Kp + l
+            // target cell (bsrc, l) of my rows has no source row when bsrc < b~_l: +Inf (:47).  This also covers
+            // levels that are unreachable at this stage (b~ clamped to B1).
+            no_src[u] = in_tab && a.r0 + row < bt;
+            // cells outside `for b = 0:B-b~` (:69) are not computed by the reference either
+            ok[u] = in_tab && row + bt < rows_left;
+        }
+        if constexpr (JSC > 0) {
+            double v[CU][JSC];
+            int g[CU][JSC];
+#pragma unroll
+            for (int u = 0; u < CU; ++u)
+#pragma unroll
+                for (int q = 0; q < JSC; ++q) {
+                    v[u][q] = pv[q * RK + x_[u]];
+                    g[u][q] = (int)pa[q * RK + x_[u]];
+                }
+            // tournament in ascending group order; on ties the earlier group stays (strict '>', HelpFunctions.jl:73).
+            // Partial minima are never NaN and carry MARK with +Inf, so this equals the sequential scan.
+#pragma unroll
+            for (int w = 1; w < JSC; w *= 2)
+#pragma unroll
+                for (int q = 0; q + w < JSC; q += 2 * w)
+#pragma unroll
+                    for (int u = 0; u < CU; ++u)
+                        if (v[u][q] > v[u][q + w]) { v[u][q] = v[u][q + w]; g[u][q] = g[u][q + w]; }
+#pragma unroll
+            for (int u = 0; u < CU; ++u) { val[u] = v[u][0]; arg[u] = g[u][0]; }
+        } else {
+#pragma unroll
+            for (int u = 0; u < CU; ++u) { val[u] = inf; arg[u] = MARKI; }
+            for (int q = 0; q < a.JS; ++q) {
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    const double v = pv[q * RK + x_[u]];
+                    const int g = (int)pa[q * RK + x_[u]];
+                    if (val[u] > v) { val[u] = v; arg[u] = g; }  // strict: earliest group wins ties
+                }
+            }
+        }
+        if (pcc) { const long long tq = clock64(); pcc[0] += tq - tq0; tq0 = tq; }
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            if (no_src[u]) Pn[x_[u]] = inf;
+            if (ok[u]) argrow[x_[u]] = (ArgT)arg[u];
+            if (ok[u] && y_[u] < RK) Pn[y_[u]] = val[u];
+            if (ok[u] && y_[u] >= RK) hring[y_[u]] = val[u];
+        }
+        if (a.phi) {  // stages 2 and 1 are the exit state (S7)
+#pragma unroll
+            for (int u = 0; u < CU; ++u)
+                if (ok[u]) a.phi[y_[u]] = val[u];
+        }
+        if (pcc) { const long long tq = clock64(); pcc[1] += tq - tq0; tq0 = tq; }
+    }
+}
+
+template <typename ArgT>
+__device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int sw, int lane)
+{
+    const int g = blockIdx.x;
+    const int r0 = g * c.R;
+    const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n, NS = c.NS;
+    const int NV = c.RB > 0 ? 2 : 1;
+    const double inf = d_inf();
+    const int btm = min(*c.btmax, B1 - 1);
+    const bool halo_on = (g > 0 && btm > 0);  // lower slices push into this one
+    const bool pushes = (g + 1 < c.G);
+    const int lblocks = Kp >> 5;
+    uint32_t cost_phase = 0, scanned_phase = 0, halo_phase = 0;
+    long long pc[3] = {0, 0, 0};  // profile (warp 0): wait for the scan, wait for halo / ring, work
+    long long pcc[2] = {0, 0};    // split of the work: loads + combine, stores
+    long long *pccp = c.prof ? pcc : nullptr;
+    long long tp = clock64();
+#define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
+    auto wait_costs = [&](long long T) {
+        const int b = (int)(T % 3);
+        mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err);
+        cost_phase ^= 1u << b;
+    };
+    auto finished = [&](int v) {
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&sm.mbar[MB_FINISHED + v]);
+            if (v == NV - 1) reds_release_inc(&sm.mbar[CNT_FINISHED]);
+        }
+    };
+
+    long long T = 0;  // global step: subproblem * n + (n - stage)
+    for (int sub = 0; sub < c.nsub; ++sub) {
+        const SlotDev sl = c.slots[sub];
+        // ---- terminal stage n (HelpFunctions.jl:27-43) = the rows stage n-1 reads:  P[b][l] = (b == b~_l(n)) ? s_l(n) : Inf
+        wait_costs(T);
+        {
+            const double *sn = sm.ss + (size_t)(T % 3) * Kp;
+            const int *bn = sm.bts + (size_t)(T % 3) * Kp;
+            double *Pw = sm.Ps + (size_t)((n - 1) & 1) * R * Kp;
+            // n == 1: only the terminal stage exists, it is the exit state (slot 1 of the reference); n == 2: it is slot 2
+            double *phi = (n == 1) ? sl.phi : (n == 2) ? sl.phi + (size_t)B1 * Kp : nullptr;
+            for (int unit = sw; unit < R * lblocks; unit += NS) {
+                const int row = unit / lblocks, l = ((unit - row * lblocks) << 5) + lane, b = r0 + row;
+                if (l < K && b < B1) {
+                    const double v = (b == bn[l]) ? sn[l] : inf;
+                    Pw[row * Kp + l] = v;
+                    if (phi) phi[(size_t)b * Kp + l] = v;
+                }
+            }
+            for (int v = 0; v < NV; ++v) finished(v);
+        }
+        ++T;
+        for (int i = n - 1; i >= 1; --i, ++T) {
+            wait_costs(T);
+            FinishArgs a;
+            a.pv = sm.pv;
+            a.pa = sm.pa;
+            a.bt = sm.bts + (size_t)(T % 3) * Kp;
+            a.Pn = sm.Ps + (size_t)((i - 1) & 1) * R * Kp;
+            a.umap = sm.umap;
+            a.hring = c.halo + ((size_t)(T % kHaloRing) * B1 + r0) * Kp;
+            a.phi = (i <= 2) ? sl.phi + ((size_t)((i + 1) & 1) * B1 + r0) * Kp : nullptr;
+            a.argrow = reinterpret_cast<unsigned char *>(sl.arg) + ((size_t)(i - 1) * B1 + r0) * Kp * sizeof(ArgT);
+            a.JS = c.JS; a.R = R; a.Kp = Kp; a.K = K; a.B1 = B1; a.r0 = r0;
+            for (int v = 0; v < NV; ++v) {
+                mbar_wait_wd(&sm.mbar[MB_SCANNED + v], (scanned_phase >> v) & 1u, c.err);
+                scanned_phase ^= 1u << v;
+                PROF_LAP(0);
+                if (v == 0) {
+                    // my next rows receive the lower slices' block by TMA (issued by the comm warp): it must have
+                    // landed before my own results overwrite the cells I produce myself
+                    if (halo_on && i >= 2) {
+                        mbar_wait_wd(&sm.mbar[MB_HALO + (i & 1)], (halo_phase >> (i & 1)) & 1u, c.err);
+                        halo_phase ^= 1u << (i & 1);
+                    }
+                    // back-pressure: the successors consumed the ring slot this step overwrites
+                    if (pushes) {
+                        unsigned int spins = 0;
+                        while ((long long)lds_acquire(&sm.mbar[RING_OK]) < T) {
+                            __nanosleep(64);
+                            if ((++spins & 0xfffffu) == 0 && *(volatile int *)&c.err[3]) break;  // the comm warp gave up
+                        }
+                    }
+                    PROF_LAP(1);
+                }
+                const int ub = v == 0 ? 0 : c.RA * lblocks, ue = v == 0 ? c.RA * lblocks : R * lblocks;
+                switch (c.JS) {
+                    case 1: finish_rows<1, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
+                    case 2: finish_rows<2, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
+                    case 4: finish_rows<4, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
+                    default: finish_rows<0, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
+                }
+                finished(v);
+                PROF_LAP(2);
+            }
+        }
+    }
+    if (c.prof && sw == 0 && lane == 0) {
+        for (int k = 0; k < 3; ++k) c.prof[(size_t)g * 16 + 5 + k] = pc[k];
+        c.prof[(size_t)g * 16 + 14] = pcc[0];
+        c.prof[(size_t)g * 16 + 15] = pcc[1];
+    }
+#undef PROF_LAP
+}
+
 // ======================================= COMM warp ===============================================
-template <int TB>
+// Event loop over three independent cursors, none of which ever blocks the others:
+//   cost:  level costs / budget uses of global step T (rows of the prep kernel's tables) into buffer T % 3 as soon
+//          as step T-3 has been finished by the scatter warps;
+//   halo:  my value rows as the lower slices pushed them during stage i, one bulk TMA straight into the rows stage
+//          i-1 reads, as soon as the predecessors have published stage i and the compute warps no longer read
+//          that buffer (they finished scanning stage i+1);
+//   ring:  how far this CTA's pushes may run ahead of the slowest successor (ring of kHaloRing slots).
+// A bounded watchdog turns a lost dependency into an error code instead of a hung GPU.
+__device__ __forceinline__ long long warp_min(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
 __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane)
 {
     const int g = blockIdx.x;
     const int r0 = g * c.R;
-    const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n;
-    const double inf = d_inf();
-    uint64_t *mb_cost = &sm.mbar[0], *mb_halo = &sm.mbar[3], *mb_full = &sm.mbar[4], *mb_done = &sm.mbar[5];
+    const int Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n, NS = c.NS;
+    const int ncw = (c.JS * c.tpg) >> 5;
     const int btm = min(*c.btmax, B1 - 1);
     const int D = (btm + R - 1) / R;  // slices a push can span
     const int my_rows = min(R, B1 - r0);  // rows of this slice that exist in the table (>= 1)
-    const bool halo_on = (g > 0 && D > 0);  // lower slices push into this one
-    const int lblocks = Kp >> 5;
-    uint32_t cost_phase = 0;  // parity bit per cost buffer
-    uint32_t done_phase = 0;
-    bool prepolled = false;  // the predecessors' counters for the stage about to be prepared were already seen
-    long long tick0 = 0;  // tick of the terminal stage of the current subproblem; stage i has tick0 + n - i
-    long long pc[7] = {0, 0, 0, 0, 0, 0, 0};  // profile: cost wait, flag wait, merge, done wait, publish, stages, halo TMA
-    long long tp = clock64();
-#define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
-    // level costs / budget uses of stage i (row i-1 of the prep kernel's tables) into buffer i%3.  Three buffers:
-    // the stage being computed, the stage being prepared, and the one in flight for the stage after that.
-    auto load_costs = [&](const SlotDev &sl, int i) {
-        const int b = i % 3;
-        mbar_expect_tx(&mb_cost[b], (uint32_t)(Kp * (sizeof(double) + sizeof(int))));
-        tma_load_1d(sm.ss + (size_t)b * Kp, sl.ss_all + (size_t)(i - 1) * Kp, (uint32_t)(Kp * sizeof(double)), &mb_cost[b]);
-        tma_load_1d(sm.bts + (size_t)b * Kp, sl.bt_all + (size_t)(i - 1) * Kp, (uint32_t)(Kp * sizeof(int)), &mb_cost[b]);
-    };
-    auto wait_costs = [&](int i) {
-        mbar_wait(&mb_cost[i % 3], (cost_phase >> (i % 3)) & 1u);
-        cost_phase ^= 1u << (i % 3);
-    };
+    const int npred = min(D, g), nsucc = min(D, c.G - 1 - g);
+    const long long Ttot = (long long)c.nsub * n;
+    // cost cursor
+    long long cT = 0;
+    int csub = 0, ck = 0;
+    // halo cursor: stage i = n - hk, hk in [1, n-2]
+    bool h_active = (npred > 0 && n >= 3);
+    int hsub = 0, hk = 1;
+    long long pred_seen = 0;
+    // ring cursor
+    long long ring_val = (c.G - 1 - g > 0) ? (long long)(kHaloRing - 1) : kNever;  // value set at kernel start
+    if (nsucc == 0 && ring_val != kNever) {  // successors exist but never receive pushes (b~ = 0 everywhere)
+        ring_val = kNever;
+        if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+    }
+    unsigned int idle = 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0};  // profile: loop trips, idle trips, pred polls, succ polls, -, steps
 
-    for (int sub = 0; sub < c.nsub; ++sub, tick0 += n) {
-        const SlotDev sl = c.slots[sub];
-        if (lane == 0) {
-            load_costs(sl, n);                  // terminal stage
-            if (n >= 2) load_costs(sl, n - 1);  // first computed stage
-        }
-        wait_costs(n);
-        if (n == 1) {
-            // only the terminal stage exists: it is the exit state (slot 1 of the reference)
-            for (int x = lane; x < my_rows * Kp; x += 32) {
-                const int row = x / Kp, l = x % Kp;
-                if (l < K) sl.phi[(size_t)(r0 + row) * Kp + l] = (r0 + row == sm.bts[Kp + l]) ? sm.ss[Kp + l] : inf;  // buffer 1 % 3
+    for (;;) {
+        bool progress = false;
+        const unsigned int fin_cnt = lds_acquire_u32(&sm.mbar[CNT_FINISHED]);  // NS arrivals per finished step
+        const unsigned int scn_cnt = lds_acquire_u32(&sm.mbar[CNT_SCANNED]);   // ncw arrivals per scanned stage
+        pc[0] += 1;
+        // ---- cost cursor --------------------------------------------------------------------------------
+        while (cT < Ttot && (cT < 3 || reached(fin_cnt, (unsigned long long)(cT - 2) * NS))) {
+            if (lane == 0) {
+                const SlotDev &sl = c.slots[csub];
+                const int b = (int)(cT % 3);
+                const int row = n - ck - 1;  // stage i = n - ck uses row i-1 of the prep tables
+                uint64_t *bar = &sm.mbar[MB_COST + b];
+                mbar_expect_tx(bar, (uint32_t)(Kp * (sizeof(double) + sizeof(int))));
+                tma_load_1d(sm.ss + (size_t)b * Kp, sl.ss_all + (size_t)row * Kp, (uint32_t)(Kp * sizeof(double)), bar);
+                tma_load_1d(sm.bts + (size_t)b * Kp, sl.bt_all + (size_t)row * Kp, (uint32_t)(Kp * sizeof(int)), bar);
             }
-            __syncwarp();
-            continue;
-        }
-
-        for (int s = n - 1; s >= 0; --s) {
-            const long long tick_s = tick0 + (n - s);  // tick of stage s
-            if (s >= 1) {
-                double *Pw = sm.Ps + (size_t)(s & 1) * R * Kp;
-                if (s == n - 1) {
-                    // ---- terminal stage n (HelpFunctions.jl:27-43) = the rows stage n-1 reads ----------------
-                    // P[b][l] = (b == b~_l(n)) ? s_l(n) : Inf
-                    const double *sn = sm.ss + (size_t)(n % 3) * Kp;
-                    const int *bn = sm.bts + (size_t)(n % 3) * Kp;
-                    for (int row = 0; row < my_rows; ++row)
-                        for (int blk = 0; blk < lblocks; ++blk) {
-                            const int l = (blk << 5) + lane, b = r0 + row;
-                            if (l < K) {
-                                const double v = (b == bn[l]) ? sn[l] : inf;
-                                Pw[row * Kp + l] = v;
-                                if (n == 2) sl.phi[((size_t)B1 + b) * Kp + l] = v;  // stage 2 is exit slot 2
-                            }
-                        }
-                    __syncwarp();
-                }
-                // ---- my value rows as the lower slices pushed them during stage s+1: one bulk TMA straight into the
-                // rows stage s reads (same row-major layout), issued first thing: the predecessors' counters were
-                // already checked at the end of the previous iteration, and these rows were released by done(s+2).
-                // The compute warps wait on mb_halo before they scatter their own stage-(s+1) results over the block.
-                if (s <= n - 2 && halo_on) {
-                    if (!prepolled) {  // not seen early (deep halo or short lag): wait for the predecessors here
-                        for (int idx = lane; idx < D; idx += 32)
-                            if (idx + 1 <= g) wait_flag(c.flags + (size_t)(g - idx - 1) * kFlagStride, tick_s - 1, c.err);
-                        __syncwarp();
-                    }
-                    if (lane == 0) {
-                        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy read
-                        const uint32_t bytes = (uint32_t)((size_t)my_rows * Kp * sizeof(double));
-                        mbar_expect_tx(mb_halo, bytes);
-                        tma_load_1d(Pw, c.halo + ((size_t)((tick_s - 1) % kHaloRing) * B1 + r0) * Kp, bytes, mb_halo);
-                    }
-                }
-                PROF_LAP(6);
-                // the buffer of stage s+2 is free (its `done` was observed in the previous iteration): prefetch s-1
-                if (lane == 0 && s - 1 >= 1) load_costs(sl, s - 1);
-                wait_costs(s);
-                PROF_LAP(0);
-                // ---- back-pressure: successors consumed the ring slot stage s will overwrite (one counter per lane) ----
-                for (int idx = lane; idx < D; idx += 32)
-                    if (g + idx + 1 < c.G)
-                        wait_flag(c.flags + (size_t)(g + idx + 1) * kFlagStride, tick_s - kHaloRing + 1, c.err);
-                // ---- look ahead: have the predecessors finished stage s already?  Then the next iteration's TMA can go
-                // out at once.  Only the comm warp's idle time is spent on this: the probing stops as soon as the compute
-                // warps finish stage s+1, so it never delays the hand-over (and cannot deadlock against back-pressure).
-                prepolled = false;
-                if (s - 1 >= 1 && halo_on) {
-                    const bool have_done_next = (s + 1 <= n - 1);
-                    for (;;) {
-                        bool ok = true;
-                        for (int idx = lane; idx < D; idx += 32)
-                            if (idx + 1 <= g && (long long)ld_relaxed(c.flags + (size_t)(g - idx - 1) * kFlagStride) < tick_s) ok = false;
-                        if (__all_sync(0xffffffffu, ok)) { prepolled = true; break; }
-                        if (!have_done_next || mbar_test(mb_done, done_phase)) break;
-                        __nanosleep(100);
-                    }
-                    if (prepolled)
-                        for (int idx = lane; idx < D; idx += 32)
-                            if (idx + 1 <= g) (void)ld_acquire(c.flags + (size_t)(g - idx - 1) * kFlagStride);
-                }
-                __syncwarp();  // every polling lane finished with an acquire load; lane 0 inherits the order through the warp sync
-                PROF_LAP(1);
-                PROF_LAP(2);
-            }
-            // ---- hand-over: wait for the compute warps to finish stage s+1, then release stage s -----------
-            const bool have_done = (s + 1 <= n - 1);
-            if (have_done) {
-                mbar_wait(mb_done, done_phase);
-                done_phase ^= 1u;
-            }
-            if (s >= 1) mbar_arrive(mb_full);
-            PROF_LAP(3);
-            // stage s+1 is complete in this CTA: hand its tick to the publisher warp, which makes the pushes visible
-            // GPU-wide, moves the progress counter and prefetches the next cost rows off this warp's critical path
-            if (have_done && lane == 0) {
-                if (c.pub) {
-                    asm volatile("st.release.cta.shared::cta.u64 [%0], %1;" ::"r"(smem_u32(&sm.mbar[6])), "l"((unsigned long long)(tick_s - 1)) : "memory");
-                } else {
-                    // long stages hide the fence: publish from here and save the extra warp
-                    fence_gpu();
-                    st_relaxed(c.flags + (size_t)g * kFlagStride, (unsigned long long)(tick_s - 1));
-                }
-            }
-            PROF_LAP(4);
+            ++cT;
+            if (++ck == n) { ck = 0; ++csub; }
+            progress = true;
             pc[5] += 1;
+        }
+        // ---- halo cursor --------------------------------------------------------------------------------
+        if (h_active) {
+            const long long hT = (long long)hsub * n + hk;
+            if (pred_seen < hT) {
+                long long m = kNever;
+                for (int idx = lane; idx < npred; idx += 32)
+                    m = min(m, (long long)ld_acquire(c.flags + (size_t)(g - idx - 1) * kFlagStride));
+                pred_seen = max(pred_seen, warp_min(m));
+                __syncwarp();  // every polling lane finished its acquire load; lane 0 inherits the order
+                pc[2] += 1;
+            }
+            // the buffer the block lands in was last read by the scan of stage i+1 (or by the previous subproblem)
+            const long long need_scanned = (long long)hsub * (n - 1) + hk - 1;
+            if (pred_seen >= hT && reached(scn_cnt, (unsigned long long)need_scanned * ncw)) {
+                if (lane == 0) {
+                    const int i = n - hk;
+                    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy read
+                    const uint32_t bytes = (uint32_t)((size_t)my_rows * Kp * sizeof(double));
+                    uint64_t *bar = &sm.mbar[MB_HALO + (i & 1)];
+                    mbar_expect_tx(bar, bytes);
+                    tma_load_1d(sm.Ps + (size_t)((i - 1) & 1) * R * Kp,
+                                c.halo + ((size_t)(hT % kHaloRing) * B1 + r0) * Kp, bytes, bar);
+                }
+                if (++hk > n - 2) { hk = 1; if (++hsub >= c.nsub) h_active = false; }
+                progress = true;
+            }
+        }
+        // ---- ring cursor --------------------------------------------------------------------------------
+        // scatter warps work on step >= cT - 3 at most cT: keep the ring bound a few steps ahead of them
+        if (ring_val < Ttot && ring_val < cT + 2) {
+            long long m = kNever;
+            for (int idx = lane; idx < nsucc; idx += 32)
+                m = min(m, (long long)ld_acquire(c.flags + (size_t)(g + idx + 1) * kFlagStride));
+            m = warp_min(m);
+            __syncwarp();
+            pc[3] += 1;
+            const long long nv = (m >= kNever) ? kNever : m + kHaloRing - 1;
+            if (nv > ring_val) {
+                ring_val = nv;
+                if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+                progress = true;
+            }
+        }
+        if (cT >= Ttot && !h_active && ring_val >= Ttot) break;
+        if (progress) { idle = 0; continue; }
+        __nanosleep(64);
+        pc[1] += 1;
+        if ((++idle & 0x3ffu) == 0) {
+            bool abort_now = *(volatile int *)&c.err[3] != 0;
+            if (!abort_now && idle > (1u << 22)) {
+                atomicOr(&c.err[2], 1);
+                atomicOr(&c.err[3], 1);
+                abort_now = true;
+            }
+            if (abort_now) {  // give up on the neighbours so that this CTA drains and the launch ends
+                pred_seen = kNever;
+                ring_val = kNever;
+                if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+            }
         }
     }
     if (c.prof && lane == 0)
-        for (int k = 0; k < 7; ++k) c.prof[(size_t)g * 16 + 8 + k] = pc[k];
-#undef PROF_LAP
+        for (int k = 0; k < 6; ++k) c.prof[(size_t)g * 16 + 8 + k] = pc[k];
 }
 
 // ===================================== PUBLISHER warp ============================================
-// Waits for the comm warp's relay (stage finished in this CTA), then: fence.acq_rel.gpu so that the pushes the
-// compute threads made during that stage are visible GPU-wide, then the relaxed store of the progress counter --
-// about 1 200 cycles that no longer sit on the comm warp's per-stage critical path.
+// Follows the scatter warps' counter; for every finished stage: fence.acq_rel.gpu so that the pushes made during
+// that stage are visible GPU-wide, then the relaxed store of the progress counter -- about 1 200 cycles that sit on
+// nobody's critical path.
 __device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane)
 {
     if (lane != 0) return;
     const int g = blockIdx.x;
     const int n = t.n;
     unsigned long long *myflag = c.flags + (size_t)g * kFlagStride;
-    long long tick0 = 0;
-    for (int sub = 0; sub < c.nsub; ++sub, tick0 += n) {
-        for (int s = n - 1; s >= 1; --s) {
-            const unsigned long long tick = (unsigned long long)(tick0 + (n - s));
-            unsigned long long seen;
+    long long T = 0;
+    for (int sub = 0; sub < c.nsub; ++sub) {
+        ++T;  // the terminal stage pushes nothing
+        for (int i = n - 1; i >= 1; --i, ++T) {
+            const unsigned long long want = (unsigned long long)(T + 1) * (unsigned)c.NS;
             unsigned int spins = 0;
-            do {
-                asm volatile("ld.acquire.cta.shared::cta.u64 %0, [%1];" : "=l"(seen) : "r"(smem_u32(&sm.mbar[6])) : "memory");
-                if (seen < tick) {
-                    __nanosleep(250);  // a quiet poll: this warp shares a scheduler with compute warps
-                    if ((++spins & 0xffffu) == 0 && *(volatile int *)&c.err[3]) return;  // watchdog fired elsewhere
-                }
-            } while (seen < tick);
+            while (!reached(lds_acquire_u32(&sm.mbar[CNT_FINISHED]), want)) {
+                __nanosleep(200);  // a quiet poll: this warp shares a scheduler with compute warps
+                if ((++spins & 0xffffu) == 0 && *(volatile int *)&c.err[3] && spins > (1u << 22)) return;  // stuck after an abort
+            }
             fence_gpu();
-            st_relaxed(myflag, tick);
+            st_relaxed(myflag, (unsigned long long)T);
         }
     }
 }
 
 // MAXT is a multiple of 128: the register file is split evenly over the four schedulers, so the per-thread
 // budget is set by the scheduler that hosts the most warps.
-template <int TB, int TL, typename ArgT, int MAXT>
+template <int TBA, int TBB, int TL, typename ArgT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 {
-    constexpr ArgT MARK = (ArgT)~(ArgT)0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem sm;
     carve(t, c, (int)sizeof(ArgT), smem_raw, &sm);
 
     const int tid = threadIdx.x;
-    const int NC = c.JS * c.tpg;  // compute threads; comm warp = threads [NC, NC+32), publisher warp = [NC+32, NC+64)
+    const int NC = c.JS * c.tpg;  // compute threads, then: comm warp, publisher warp, NS scatter warps
     const int g = blockIdx.x;
-    const int r0 = g * c.R;
-    const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n;
+    const int K = t.K, Kp = t.Kp, R = c.R, n = t.n;
+    constexpr int NV = TBB > 0 ? 2 : 1;
     const double inf = d_inf();
-    uint64_t *mb_full = &sm.mbar[4], *mb_done = &sm.mbar[5];
 
-    // one-time: jump costs into shared memory, value rows and halo staging to +Inf, barriers
+    // one-time: jump costs into shared memory, value rows to +Inf, barriers and counters
     for (int x = tid; x < K * Kp; x += blockDim.x) sm.cs[x] = t.cost[x];
     for (int x = tid; x < 2 * R * Kp; x += blockDim.x) sm.Ps[x] = inf;
+    for (int x = tid; x < R * (Kp >> 5); x += blockDim.x) sm.umap[x] = ((x / (Kp >> 5)) << 16) | ((x % (Kp >> 5)) << 5);
     if (tid == 0) {
-        mbar_init(&sm.mbar[0], 1);
-        mbar_init(&sm.mbar[1], 1);
-        mbar_init(&sm.mbar[2], 1);
-        mbar_init(&sm.mbar[3], 1);
-        mbar_init(mb_full, 32);
-        mbar_init(mb_done, NC);
-        sm.mbar[6] = 0;  // relay counter
+        for (int k = 0; k < 5; ++k) mbar_init(&sm.mbar[k], 1);  // cost[3], halo[2]: one arming arrival + tx bytes
+        for (int v = 0; v < 2; ++v) {
+            mbar_init(&sm.mbar[MB_SCANNED + v], NC >> 5);
+            mbar_init(&sm.mbar[MB_FINISHED + v], c.NS);
+        }
+        sm.mbar[CNT_SCANNED] = 0;
+        sm.mbar[CNT_FINISHED] = 0;
+        sm.mbar[RING_OK] = (g + 1 < c.G) ? (uint64_t)(kHaloRing - 1) : (uint64_t)kNever;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (tid >= NC + 32) {  // only launched when c.pub
+    if (tid >= NC + 64) {
+        scatter_warp<ArgT>(t, c, sm, (tid - NC - 64) >> 5, tid & 31);
+        return;
+    }
+    if (tid >= NC + 32) {
         publisher_warp(t, c, sm, tid - NC - 32);
         return;
     }
     if (tid >= NC) {
-        comm_warp<TB>(t, c, sm, tid - NC);
+        comm_warp(t, c, sm, tid - NC);
         return;
     }
 
@@ -448,151 +672,113 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     const int lg = active ? tig % c.nLG : 0;
     const int jb = jg * c.jper;
     const int je = min(K, jb + c.jper);
-    uint32_t full_phase = 0, halo_phase = 0;
-    long long tick0 = 0;
-    const int btm_c = min(*c.btmax, B1 - 1);
-    const bool halo_on = (g > 0 && btm_c > 0);  // same condition as the comm warp's (D > 0)
-    uint64_t *mb_halo = &sm.mbar[3];
-    long long pc[5] = {0, 0, 0, 0, 0};  // profile: full wait, phase B, barrier, phase C, stages
-    long long pcc[3] = {0, 0, 0};       // phase C split: halo wait, combine, scatter
-    long long tpc = 0;
+    const int lane = tid & 31;
+    uint32_t cost_phase = 0, fin_phase = 0;
+    long long pc[5] = {0, 0, 0, 0, 0};  // profile: wait A (+ costs), phase B, hand-over, wait B, stages
     long long tp = clock64();
 #define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
+    auto wait_costs = [&](long long T) {
+        const int b = (int)(T % 3);
+        mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err);
+        cost_phase ^= 1u << b;
+    };
+    auto wait_finished = [&](int v) {
+        mbar_wait_wd(&sm.mbar[MB_FINISHED + v], (fin_phase >> v) & 1u, c.err);
+        fin_phase ^= 1u << v;
+    };
+    auto scanned = [&](int v) {
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&sm.mbar[MB_SCANNED + v]);
+            if (v == NV - 1) reds_release_inc(&sm.mbar[CNT_SCANNED]);
+        }
+    };
+    const int rowA = rg * TBA, rowB = c.RA + rg * TBB;
+    ArgT *pa = reinterpret_cast<ArgT *>(sm.pa);
 
-    for (int sub = 0; sub < c.nsub; ++sub, tick0 += n) {
-        const SlotDev sl = c.slots[sub];
-        ArgT *argtab = reinterpret_cast<ArgT *>(sl.arg);
-        for (int i = n - 1; i >= 1; --i) {
-            const long long tick = tick0 + (n - i);
+    long long T = 0;
+    for (int sub = 0; sub < c.nsub; ++sub) {
+        wait_costs(T);  // terminal stage: nothing to scan, but every role follows every cost phase
+        ++T;
+        for (int i = n - 1; i >= 1; --i, ++T) {
             const double *Pc = sm.Ps + (size_t)(i & 1) * R * Kp;
-            double *Pn = sm.Ps + (size_t)((i - 1) & 1) * R * Kp;
-            const double *ssc = sm.ss + (size_t)(i % 3) * Kp;
-            const int *bt_cur = sm.bts + (size_t)(i % 3) * Kp;
-
-            mbar_wait(mb_full, full_phase);  // rows, stage costs and back-pressure for stage i are ready
-            full_phase ^= 1u;
+            const double *ssc = sm.ss + (size_t)(T % 3) * Kp;
+            wait_costs(T);
+            // ---- phase B: register-tiled min-plus scan over this group's successors, sub-slice A then B ------
+            wait_finished(0);  // rows of A for stage i are complete (finish(A, i+1) or the terminal stage)
             PROF_LAP(0);
-
-            // ---- phase B: register-tiled min-plus scan over this group's successors (values only) --------
             if (active)
-                phase_b<TB, TL, ArgT>(Pc + (size_t)rg * TB * Kp, sm.cs + lg * TL, ssc + lg * TL,
-                                      sm.pv + ((size_t)jg * R + rg * TB) * Kp + lg * TL,
-                                      reinterpret_cast<ArgT *>(sm.pa) + ((size_t)jg * R + rg * TB) * Kp + lg * TL, jb, je,
-                                      Kp);
+                phase_b<TBA, TL, ArgT>(Pc + (size_t)rowA * Kp, sm.cs + lg * TL, ssc + lg * TL,
+                                       sm.pv + ((size_t)jg * R + rowA) * Kp + lg * TL,
+                                       pa + ((size_t)jg * R + rowA) * Kp + lg * TL, jb, je, Kp);
             PROF_LAP(1);
-            compute_barrier(NC);
+            scanned(0);
             PROF_LAP(2);
-
-            // ---- phase C: combine the j-groups in ascending order, scatter the value, store the argmin --------
-            // Work unit = 32 consecutive levels of one source row (a warp-wide, coalesced row segment); every warp
-            // handles up to CU units at once so that the dependent compare chains of different cells overlap.
-            {
-                constexpr int CU = 4;
-                // ring slot of this stage's pushes: value rows [B1][Kp], row-major like the rows in shared memory
-                double *hring = c.halo + (size_t)(tick % kHaloRing) * B1 * Kp;
-                // my next rows receive the lower slices' block by TMA (issued by the comm warp): it must have landed
-                // before my own results overwrite the cells I produce myself
-                if (c.prof) tpc = clock64();
-                if (halo_on && i - 1 >= 1 && i - 1 <= n - 2) {
-                    mbar_wait(mb_halo, halo_phase);
-                    halo_phase ^= 1u;
-                }
-                if (c.prof) { const long long tq = clock64(); pcc[0] += tq - tpc; tpc = tq; }
-                const ArgT *pa_all = reinterpret_cast<const ArgT *>(sm.pa);
-                const int lblocks = Kp >> 5;
-                const int units = R * lblocks;
-                const int warp = tid >> 5, lane = tid & 31, nwarps = NC >> 5;
-                for (int u0 = warp; u0 < units; u0 += nwarps * CU) {
-                    double val[CU];
-                    int row_[CU], l_[CU], tgt_[CU], arg_[CU];
-                    bool ok[CU], live_[CU];
-#pragma unroll
-                    for (int u = 0; u < CU; ++u) {
-                        const int unit = u0 + u * nwarps;
-                        const bool live = unit < units;
-                        const int row = live ? unit / lblocks : 0;
-                        const int l = live ? ((unit - row * lblocks) << 5) + lane : lane;
-                        const int bsrc = r0 + row;
-                        const int tgt = bsrc + bt_cur[l];
-                        // cells outside `for b = 0:B-b~` (:69) are not computed by the reference either
-                        ok[u] = live && l < K && bsrc < B1 && tgt < B1;
-                        live_[u] = live;
-                        row_[u] = row; l_[u] = l; tgt_[u] = tgt;
-                        val[u] = inf; arg_[u] = (int)MARK;
-                    }
-                    for (int q = 0; q < c.JS; ++q) {
-#pragma unroll
-                        for (int u = 0; u < CU; ++u) {
-                            const size_t x = ((size_t)q * R + row_[u]) * Kp + l_[u];
-                            const double v = sm.pv[x];
-                            if (val[u] > v) { val[u] = v; arg_[u] = (int)pa_all[x]; }  // strict: earliest group wins ties
-                        }
-                    }
-                    if (c.prof) { const long long tq = clock64(); pcc[1] += tq - tpc; tpc = tq; }
-#pragma unroll
-                    for (int u = 0; u < CU; ++u) {
-                        // target cell (bsrc, l) of my rows has no source row when bsrc < b~_l: +Inf (:47).  This also
-                        // covers levels that are unreachable at this stage (b~ clamped to B1).
-                        if (live_[u] && l_[u] < K && r0 + row_[u] < B1 && r0 + row_[u] < tgt_[u] - (r0 + row_[u]))
-                            Pn[row_[u] * Kp + l_[u]] = inf;
-                        if (!ok[u]) continue;
-                        const int bsrc = r0 + row_[u];
-                        argtab[((size_t)(i - 1) * B1 + bsrc) * Kp + l_[u]] = (ArgT)arg_[u];
-                        if (tgt_[u] < r0 + R) Pn[(tgt_[u] - r0) * Kp + l_[u]] = val[u];
-                        else hring[(size_t)tgt_[u] * Kp + l_[u]] = val[u];
-                        if (i <= 2) sl.phi[((size_t)((i + 1) & 1) * B1 + tgt_[u]) * Kp + l_[u]] = val[u];
-                    }
-                }
+            if constexpr (TBB > 0) {
+                wait_finished(1);
+                PROF_LAP(3);
+                if (active)
+                    phase_b<TBB, TL, ArgT>(Pc + (size_t)rowB * Kp, sm.cs + lg * TL, ssc + lg * TL,
+                                           sm.pv + ((size_t)jg * R + rowB) * Kp + lg * TL,
+                                           pa + ((size_t)jg * R + rowB) * Kp + lg * TL, jb, je, Kp);
+                PROF_LAP(1);
+                scanned(1);
+                PROF_LAP(2);
             }
-            if (c.prof) { const long long tq = clock64(); pcc[2] += tq - tpc; tpc = tq; }
-            mbar_arrive(mb_done);
-            PROF_LAP(3);
             pc[4] += 1;
         }
+        // drain: stage 1 (or the terminal stage when n == 1) is finished; keeps the barrier phases aligned
+        for (int v = 0; v < NV; ++v) wait_finished(v);
     }
-    if (c.prof && tid == 0)
-        for (int k = 0; k < 5; ++k) c.prof[(size_t)g * 16 + k] = pc[k];
-    if (c.prof && tid == 0) {  // phase C split of warp 0: halo wait, combine, scatter
-        c.prof[(size_t)g * 16 + 5] = pcc[0];
-        c.prof[(size_t)g * 16 + 6] = pcc[1];
-        c.prof[(size_t)g * 16 + 7] = pcc[2];
+    if (c.prof && tid == 0) {
+        c.prof[(size_t)g * 16 + 0] = pc[0];
+        c.prof[(size_t)g * 16 + 1] = pc[1];
+        c.prof[(size_t)g * 16 + 2] = pc[2];
+        c.prof[(size_t)g * 16 + 3] = pc[3];
+        c.prof[(size_t)g * 16 + 4] = pc[4];
     }
 #undef PROF_LAP
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-struct Variant { int TB, TL, maxt; };
-// Large register tiles run with 8 compute warps (224 registers per thread); small tiles with up to 16 compute
-// warps (120 registers per thread), which hides the FP64 compare->select latency with more warps in flight.
-static const Variant kVariants[] = {{7, 4, kWaveThreadsBig},   {8, 4, kWaveThreadsBig},   {4, 4, kWaveThreadsSmall},
-                                    {7, 2, kWaveThreadsSmall}, {8, 2, kWaveThreadsSmall}, {8, 1, kWaveThreadsSmall},
-                                    {4, 1, kWaveThreadsSmall}};
+struct Variant { int TBA, TBB, TL; };
+// (rows of sub-slice A, rows of sub-slice B, levels) per thread tile.  Every variant is built for CTAs of up to 512
+// threads (128 registers per thread: no spills, and room for the scatter warps that hide phase C).
+static const Variant kVariants[] = {{4, 3, 2}, {4, 4, 2}, {3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 1, 2}, {1, 1, 2},
+                                    {1, 0, 2}, {4, 4, 1}, {3, 3, 1}, {2, 2, 1}, {1, 1, 1}, {1, 0, 1}};
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kWaveThreads = kWaveThreadsSmall;
 
-static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int pub, WaveCfg &c)
+static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int NS, WaveCfg &c)
 {
-    c.pub = pub;
     c.variant = v;
-    c.TB = kVariants[v].TB;
+    c.TB = kVariants[v].TBA;
+    c.TBB = kVariants[v].TBB;
     c.TL = kVariants[v].TL;
+    const int tb = c.TB + c.TBB;
     const int rows_per_cta = (t.B1 + G - 1) / G;
-    c.RG = (rows_per_cta + c.TB - 1) / c.TB;
-    c.R = c.RG * c.TB;
+    c.RG = (rows_per_cta + tb - 1) / tb;
+    c.R = c.RG * tb;
+    c.RA = c.RG * c.TB;
+    c.RB = c.RG * c.TBB;
     c.G = (t.B1 + c.R - 1) / c.R;  // drop CTAs that would own no row
     c.nLG = (t.K + c.TL - 1) / c.TL;
     c.JS = JS;
     c.jper = ((t.K + JS - 1) / JS + 1) & ~1;  // even: successors are taken in aligned pairs
     c.tpg = ((c.RG * c.nLG + 31) / 32) * 32;
-    c.RP = c.R;
-    c.threads = c.JS * c.tpg + 32 + 32 * c.pub;  // + the comm warp (+ the publisher warp)
+    c.NS = NS;
+    c.threads = c.JS * c.tpg + 64 + 32 * NS;  // + comm warp + publisher warp + scatter warps
     c.smem = carve(t, c, argw, nullptr, nullptr);
 }
 
 bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int want_ctas, int want_js,
                     int want_variant, WaveCfg &cfg)
 {
-    if (t.M > kMaxM || t.K > 4096) return false;
-    double best_score = -1.;
+    if (t.M > kMaxM || argw != 1) return false;  // K > 255: the jump-cost table would not fit in shared memory anyway
+    const int want_ns = want_variant / 100;
+    want_variant %= 100;
+    static const int kNsChoices[] = {1, 2, 3, 4, 6, 8};
+    double best_stage = -1.;
     bool found = false;
     for (int v = 0; v < kNumVariants; ++v) {
         if (want_variant > 0 && v != want_variant - 1) continue;
@@ -600,34 +786,51 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
         for (int js = 1; js <= 16; ++js) {
             if (want_js > 0 && js != want_js) continue;
             if (js > t.K) break;
-            int gmax = want_ctas > 0 ? want_ctas : num_sms;
-            if (gmax > num_sms) gmax = num_sms;
-            WaveCfg c = cfg;
-            fill_geometry(t, argw, gmax, js, v, 0, c);
-            if (c.threads > kVariants[v].maxt || c.threads < 64) continue;
-            if (c.smem > smem_max) continue;
-            // Cost model per stage and CTA in scheduler cycles, fitted to the in-kernel profile on B200
-            // (profiles/phase_profile_r01.txt).  Phase B is issue bound: an FP64 instruction takes two issue slots,
-            // so a candidate costs DADD(2)+DSETP(2)+2 FSEL+SEL = 7 slots, plus the per-successor loads and the
-            // s_l + c_jl adds; the busiest scheduler hosts ceil(warps/4) warps; ~25% of the slots are lost to
-            // dependency stalls.  Phase C (combine + scatter) is latency bound and grows with the j-split.
-            const double warps = (double)(c.threads - 32) / 32.0;
-            const double tile = (double)(c.TB * c.TL);
-            const double per_j = 7.0 * tile + 2.0 * c.TL + ((c.TB + 1) / 2) + ((c.TL + 1) / 2) + 3.0;
-            const double b_cycles = per_j * c.jper * (double)(((int)warps + 3) / 4) * 1.25;
-            const double units = (double)c.R * (t.Kp / 32);
-            const double batches = (double)(((int)units + (int)warps * 4 - 1) / ((int)warps * 4));
-            const double c_cycles = batches * (1500.0 + 300.0 * js);
-            const double stage = b_cycles + c_cycles + 600.0;
-            const double score = 1.0 / stage;  // every CTA does the same work per stage: smaller is better
-            if (score > best_score) {
-                best_score = score;
-                cfg = c;
-                found = true;
-                // short stages cannot hide the ~1 200-cycle publish fence behind compute: give it its own warp
-                if (stage < 9000.0 && c.threads + 32 <= kVariants[v].maxt) {
-                    cfg.pub = 1;
-                    cfg.threads += 32;
+            for (int nsi = 0; nsi < 6; ++nsi) {
+                const int ns = kNsChoices[nsi];
+                if (want_ns > 0 && ns != want_ns) continue;
+                int gmax = want_ctas > 0 ? want_ctas : num_sms;
+                if (gmax > num_sms) gmax = num_sms;
+                WaveCfg c = cfg;
+                fill_geometry(t, argw, gmax, js, v, ns, c);
+                if (c.threads > kWaveThreads) continue;
+                if (c.smem > smem_max) continue;
+                if ((size_t)c.JS * c.R * t.Kp >= ((size_t)1 << 30) || (size_t)t.B1 * t.Kp >= ((size_t)1 << 31) ||
+                    c.R >= (1 << 15) || t.Kp >= (1 << 16))
+                    continue;  // 32-bit cell indices in phase C
+                // Cost model per stage and CTA in scheduler cycles, fitted to the in-kernel profile on B200
+                // (profiles/phase_profile_r01.txt).  Phase B is issue bound: an FP64 instruction takes two issue
+                // slots, so a candidate costs DADD(2)+DSETP(2)+2 FSEL+SEL = 7 slots, plus the per-successor loads and
+                // the s_l + c_jl adds; the busiest scheduler hosts ceil(warps/4) warps; ~20% of the slots are lost to
+                // dependency stalls.  Phase C is latency bound; it only shows when it outlasts the scan of the other
+                // sub-slice that hides it.
+                const int cwarps = c.JS * c.tpg / 32;
+                const int sched = (cwarps + 3) / 4;
+                const double stall = sched == 1 ? 1.5 : sched == 2 ? 1.3 : 1.2;  // fewer warps hide less latency
+                auto scan = [&](int tb) {
+                    if (tb == 0) return 0.0;
+                    const double per_j = 7.0 * tb * c.TL + 2.0 * c.TL + ((tb + 1) / 2) + ((c.TL + 1) / 2) + 3.0;
+                    return per_j * c.jper * sched * stall + 150.0;
+                };
+                // a batch of four units per scatter warp; the scatter warps only get the issue slots the scan leaves
+                auto finish = [&](int rows, bool hidden) {
+                    const int units = rows * (t.Kp / 32);
+                    const int batches = (units + ns * 4 - 1) / (ns * 4);
+                    return batches * (hidden ? 1200.0 + 450.0 * js : 450.0 + 120.0 * js) + 150.0;
+                };
+                const double sa = scan(c.TB), sb = scan(c.TBB);
+                double stage;
+                if (c.TBB > 0) {
+                    const double fa = finish(c.RA, true), fb = finish(c.RB, true);
+                    stage = sa + sb + (fa > sb ? fa - sb : 0.) + (fb > sa ? fb - sa : 0.);
+                } else {
+                    stage = sa + finish(c.RA, false);
+                }
+                stage += 25.0 * ns;  // scatter warps take issue slots from the scan
+                if (!found || stage < best_stage) {
+                    best_stage = stage;
+                    cfg = c;
+                    found = true;
                 }
             }
         }
@@ -635,36 +838,34 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
     return found;
 }
 
-template <int TB, int TL, int MAXT>
-static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, int argw, cudaStream_t st)
+template <int TBA, int TBB, int TL>
+static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStream_t st)
 {
     void *args[] = {(void *)&t, (void *)&cfg};
-    const void *fn = (argw == 1) ? (const void *)wavefront_kernel<TB, TL, uint8_t, MAXT>
-                                 : (const void *)wavefront_kernel<TB, TL, uint16_t, MAXT>;
+    const void *fn = (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, kWaveThreads>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     // cooperative launch: the CTAs wait on one another, so all of them must be co-resident
     return cudaLaunchCooperativeKernel(fn, dim3(cfg.G), dim3(cfg.threads), args, cfg.smem, st);
 }
 
-// Small tiles are compiled for two CTA sizes: up to 384 threads (168 registers per thread) and up to 512 (128).
-template <int TB, int TL>
-static cudaError_t launch_small(const Tables &t, const WaveCfg &cfg, int argw, cudaStream_t st)
-{
-    if (cfg.threads <= kWaveThreadsMid) return launch_variant<TB, TL, kWaveThreadsMid>(t, cfg, argw, st);
-    return launch_variant<TB, TL, kWaveThreadsSmall>(t, cfg, argw, st);
-}
-
 cudaError_t launch_wavefront(const Tables &t, const WaveCfg &cfg, int argw, cudaStream_t st)
 {
+    if (argw != 1) return cudaErrorInvalidValue;
     switch (cfg.variant) {
-        case 0: return launch_variant<7, 4, kWaveThreadsBig>(t, cfg, argw, st);
-        case 1: return launch_variant<8, 4, kWaveThreadsBig>(t, cfg, argw, st);
-        case 2: return launch_small<4, 4>(t, cfg, argw, st);
-        case 3: return launch_small<7, 2>(t, cfg, argw, st);
-        case 4: return launch_small<8, 2>(t, cfg, argw, st);
-        case 5: return launch_small<8, 1>(t, cfg, argw, st);
-        case 6: return launch_small<4, 1>(t, cfg, argw, st);
+        case 0: return launch_variant<4, 3, 2>(t, cfg, st);
+        case 1: return launch_variant<4, 4, 2>(t, cfg, st);
+        case 2: return launch_variant<3, 3, 2>(t, cfg, st);
+        case 3: return launch_variant<3, 2, 2>(t, cfg, st);
+        case 4: return launch_variant<2, 2, 2>(t, cfg, st);
+        case 5: return launch_variant<2, 1, 2>(t, cfg, st);
+        case 6: return launch_variant<1, 1, 2>(t, cfg, st);
+        case 7: return launch_variant<1, 0, 2>(t, cfg, st);
+        case 8: return launch_variant<4, 4, 1>(t, cfg, st);
+        case 9: return launch_variant<3, 3, 1>(t, cfg, st);
+        case 10: return launch_variant<2, 2, 1>(t, cfg, st);
+        case 11: return launch_variant<1, 1, 1>(t, cfg, st);
+        case 12: return launch_variant<1, 0, 1>(t, cfg, st);
         default: return cudaErrorInvalidValue;
     }
 }

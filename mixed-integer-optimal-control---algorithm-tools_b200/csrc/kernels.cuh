@@ -16,18 +16,19 @@ void launch_tv(const Tables &t, const SlotDev &slot, int mode, double *out, cuda
 
 // kernel_wavefront.cu -- the persistent pipelined DP
 struct WaveCfg {
-    int variant;  // index into the (TB, TL) instantiation table
-    int TB, TL;   // source rows / levels per thread tile
+    int variant;  // index into the tile instantiation table
+    int TB, TBB;  // source rows per thread tile in sub-slice A / sub-slice B (TBB = 0: one sub-slice)
+    int TL;       // levels per thread tile
     int G;        // CTAs (each owns R consecutive source budget rows)
-    int RG;       // row groups per CTA
-    int R;        // RG * TB
+    int RG;       // row groups per sub-slice
+    int R;        // RA + RB
+    int RA, RB;   // rows of sub-slice A (lower) and B (upper): RG * TB, RG * TBB
     int nLG;      // level groups = ceil(K / TL)
     int JS;       // j-split: thread groups scanning disjoint successor ranges
-    int jper;     // successors per group = ceil(K / JS)
+    int jper;     // successors per group = ceil(K / JS), rounded up to even
     int tpg;      // threads per group (multiple of 32)
-    int RP;       // padded row positions per level in the shared value rows
-    int pub;      // 1: a separate publisher warp moves the progress counter (stages too short to hide the fence)
-    int threads;  // JS * tpg
+    int NS;       // scatter warps (phase C)
+    int threads;  // JS * tpg compute threads + comm warp + publisher warp + NS scatter warps
     size_t smem;  // dynamic shared memory bytes
     int nsub;     // subproblems walked by this launch
     const SlotDev *slots;  // device array [nsub]
@@ -39,7 +40,8 @@ struct WaveCfg {
 };
 
 // Fills the geometry fields of cfg for the given tables; returns false when the shape cannot run on the
-// wavefront kernel (e.g. the jump-cost table does not fit in shared memory).
+// wavefront kernel (e.g. the jump-cost table does not fit in shared memory).  want_variant = 0 picks the tile by
+// the cost model, v > 0 forces tile v - 1; adding 100 * NS forces the number of scatter warps.
 bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int want_ctas,
                     int want_js, int want_variant, WaveCfg &cfg);
 cudaError_t launch_wavefront(const Tables &t, const WaveCfg &cfg, int argw, cudaStream_t st);

@@ -128,11 +128,14 @@ def test_synthetic_config4_shape_vs_oracle(gpu_lib, oracle, tie):
     assert st["ctas"] >= 100  # the pipelined path really spreads over the GPU
 
 
-@pytest.mark.parametrize("tune", [dict(ctas=8, jsplit=1), dict(ctas=5, jsplit=2), dict(ctas=16, jsplit=5, variant=2),
+@pytest.mark.parametrize("tune", [dict(ctas=8, jsplit=1), dict(ctas=20, jsplit=2), dict(ctas=16, jsplit=3, variant=2),
                                   dict(ctas=40, jsplit=3, variant=4), dict(ctas=148, jsplit=6, variant=1),
-                                  dict(jsplit=1, variant=6), dict(ctas=9, variant=3)])
+                                  dict(jsplit=1, variant=6), dict(ctas=9, variant=3), dict(variant=5),
+                                  dict(variant=107), dict(variant=408), dict(ctas=30, variant=9), dict(variant=10),
+                                  dict(variant=311), dict(variant=12), dict(variant=413, jsplit=2)])
 def test_wavefront_geometries(gpu_lib, oracle, tune):
-    """Every tile variant / CTA count / j-split of the pipelined kernel gives identical bits."""
+    """Every tile variant / CTA count / j-split / scatter-warp count (variant + 100 * NS) of the pipelined kernel
+    gives identical bits."""
     wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
     inst = wl.synthetic(n=70, B=211, seed=77, levels=4, M=3, tie_heavy=True)   # K = 64
     check_against_oracle(gpu_lib, oracle, inst.nu, inst.iterator, inst.n, inst.B, inst.df, inst.u_old, inst.beta,

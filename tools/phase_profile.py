@@ -1,5 +1,5 @@
 """Prints the in-kernel cycle breakdown of the wavefront kernel (bb200_profile) on config-4-shaped input.
-Usage: python tools/phase_profile.py [n] [ctas jsplit variant]"""
+Usage: python tools/phase_profile.py [n] [ctas jsplit variant] [kind]"""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -19,16 +19,20 @@ plan.bellman_resident(0, 1); plan.sync()
 st = plan.stats()
 prof = plan.profile(True, fetch=True)
 G = int(st["ctas"])
-print(f"{kind} n={n} K={inst.K} B={inst.B} variant={int(st.get('variant', -1))} ctas={G} rows={int(st['rows_per_cta'])} threads={int(st['threads'])} js={int(st['jsplit'])} wave_ms={st['wave_ms']:.3f} "
+print(f"{kind} n={n} K={inst.K} B={inst.B} variant={int(st['variant'])} ctas={G} rows={int(st['rows_per_cta'])} threads={int(st['threads'])} "
+      f"js={int(st['jsplit'])} ns={int(st['scatter_warps'])} wave_ms={st['wave_ms']:.3f} "
       f"us/stage={st['wave_ms']*1e3/(n-1):.2f}  T upd/s={plan.count_updates()/st['wave_ms']/1e9:.3f}")
-names_c = ["wait_full", "phaseB", "barrier", "phaseC"]
-names_m = ["eval", "flagwait", "merge", "donewait", "publish"]
-for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
-    row = prof[gsel]
+names_c = ["waitA", "phaseB", "handover", "waitB"]
+names_s = ["wait_scan", "wait_halo_ring", "phaseC"]
+names_x = ["C_combine", "C_store"]
+names_m = ["trips", "idle", "pred_polls", "succ_polls"]
+def line(row):
     stg = max(row[4], 1)
-    print(f"cta {gsel:3d} compute cyc/stage: " + "  ".join(f"{nm}={row[k]/stg:8.0f}" for k, nm in enumerate(names_c)) +
-          f" | comm: " + "  ".join(f"{nm}={row[8+k]/max(row[13],1):8.0f}" for k, nm in enumerate(names_m)))
-avg = prof[:G].mean(axis=0)
-print("phase C split cyc/stage: halo wait=%d combine=%d scatter=%d" % tuple(round(avg[k]/max(avg[4],1)) for k in (5,6,7)))
-print("comm halo TMA wait cyc/stage:", round(avg[14]/max(avg[13],1)))
-print("avg compute:", {nm: round(avg[k]/max(avg[4],1)) for k, nm in enumerate(names_c)}, "comm:", {nm: round(avg[8+k]/max(avg[13],1)) for k, nm in enumerate(names_m)})
+    return ("compute: " + " ".join(f"{nm}={row[k]/stg:7.0f}" for k, nm in enumerate(names_c)) +
+            " | scatter: " + " ".join(f"{nm}={row[5+k]/stg:7.0f}" for k, nm in enumerate(names_s)) +
+            " (" + " ".join(f"{nm}={row[14+k]/stg:6.0f}" for k, nm in enumerate(names_x)) + ")" +
+            " | comm/stage: " + " ".join(f"{nm}={row[8+k]/stg:6.2f}" for k, nm in enumerate(names_m)))
+for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
+    if 0 <= gsel < G:
+        print(f"cta {gsel:3d} " + line(prof[gsel]))
+print("avg     " + line(prof[:G].mean(axis=0)))
