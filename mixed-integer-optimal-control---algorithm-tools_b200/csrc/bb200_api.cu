@@ -18,6 +18,7 @@
 #include "../../include/bellman_b200.h"
 #include "bb200_internal.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 
 using namespace bb200;
 
@@ -205,6 +206,7 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false)
         c.err = p->d_err;
         c.btmax = p->d_btmax;
         c.prof = p->prof_on ? p->d_prof : nullptr;
+        c.decouple = (p->prof_on && getenv("BELLMAN_B200_DECOUPLE")) ? 1 : 0;  // profiling experiment, never a result
         if (!capturing) CU(cudaEventRecord(p->ev[4], st));
         CU(launch_wavefront(p->tab, c, p->argw, st));
         if (!capturing) CU(cudaEventRecord(p->ev[5], st));

@@ -355,22 +355,100 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
     }
 }
 
+// Phase C and the terminal stage for the rows of one CTA, executed by NF "finisher" warps: the scatter warps, or --
+// for tiles without a second sub-slice -- the compute warps themselves after their scan.
+template <typename ArgT>
+struct Finisher {
+    const Tables &t;
+    const WaveCfg &c;
+    const Smem &sm;
+    const int fw, NF, lane;  // this warp's index among the NF finisher warps
+    const int r0, lblocks;
+    bool halo_on, pushes;
+    uint32_t halo_phase = 0;
+    long long pcc[2] = {0, 0};  // profile: loads + combine, stores
+
+    __device__ __forceinline__ Finisher(const Tables &t_, const WaveCfg &c_, const Smem &sm_, int fw_, int NF_, int lane_)
+        : t(t_), c(c_), sm(sm_), fw(fw_), NF(NF_), lane(lane_), r0(blockIdx.x * c_.R), lblocks(t_.Kp >> 5)
+    {
+        const int btm = min(*c.btmax, t.B1 - 1);
+        halo_on = (blockIdx.x > 0 && btm > 0);  // lower slices push into this one
+        pushes = (blockIdx.x + 1 < (unsigned)c.G);
+    }
+
+    // terminal stage n (HelpFunctions.jl:27-43) = the rows stage n-1 reads:  P[b][l] = (b == b~_l(n)) ? s_l(n) : Inf
+    __device__ __forceinline__ void terminal(const SlotDev &sl, long long T)
+    {
+        const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n;
+        const double inf = d_inf();
+        const double *sn = sm.ss + (size_t)(T % 3) * Kp;
+        const int *bn = sm.bts + (size_t)(T % 3) * Kp;
+        double *Pw = sm.Ps + (size_t)((n - 1) & 1) * R * Kp;
+        // n == 1: only the terminal stage exists, it is the exit state (slot 1 of the reference); n == 2: it is slot 2
+        double *phi = (n == 1) ? sl.phi : (n == 2) ? sl.phi + (size_t)B1 * Kp : nullptr;
+        for (int unit = fw; unit < R * lblocks; unit += NF) {
+            const int row = unit / lblocks, l = ((unit - row * lblocks) << 5) + lane, b = r0 + row;
+            if (l < K && b < B1) {
+                const double v = (b == bn[l]) ? sn[l] : inf;
+                Pw[row * Kp + l] = v;
+                if (phi) phi[(size_t)b * Kp + l] = v;
+            }
+        }
+    }
+
+    // before the first store of stage i: halo rows landed, ring slot free
+    __device__ __forceinline__ void wait_inputs(int i, long long T)
+    {
+        // my next rows receive the lower slices' block by TMA (issued by the comm warp): it must have landed before
+        // my own results overwrite the cells I produce myself
+        if (halo_on && i >= 2) {
+            mbar_wait_wd(&sm.mbar[MB_HALO + (i & 1)], (halo_phase >> (i & 1)) & 1u, c.err);
+            halo_phase ^= 1u << (i & 1);
+        }
+        // back-pressure: the successors consumed the ring slot this step overwrites
+        if (pushes) {
+            unsigned int spins = 0;
+            while ((long long)lds_acquire(&sm.mbar[RING_OK]) < T) {
+                __nanosleep(64);
+                if ((++spins & 0xfffffu) == 0 && *(volatile int *)&c.err[3]) break;  // the comm warp gave up
+            }
+        }
+    }
+
+    // phase C of work units [ub, ue) of stage i (global step T)
+    __device__ __forceinline__ void rows(const SlotDev &sl, int i, long long T, int ub, int ue)
+    {
+        const int Kp = t.Kp, B1 = t.B1, R = c.R;
+        FinishArgs a;
+        a.pv = sm.pv;
+        a.pa = sm.pa;
+        a.bt = sm.bts + (size_t)(T % 3) * Kp;
+        a.umap = sm.umap;
+        a.Pn = sm.Ps + (size_t)((i - 1) & 1) * R * Kp;
+        a.hring = c.halo + ((size_t)(T % kHaloRing) * B1 + r0) * Kp;
+        a.phi = (i <= 2) ? sl.phi + ((size_t)((i + 1) & 1) * B1 + r0) * Kp : nullptr;
+        a.argrow = reinterpret_cast<unsigned char *>(sl.arg) + ((size_t)(i - 1) * B1 + r0) * Kp * sizeof(ArgT);
+        a.JS = c.JS; a.R = R; a.Kp = Kp; a.K = t.K; a.B1 = B1; a.r0 = r0;
+        long long *pccp = c.prof ? pcc : nullptr;
+        switch (c.JS) {
+            case 1: finish_rows<1, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
+            case 2: finish_rows<2, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
+            case 4: finish_rows<4, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
+            default: finish_rows<0, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
+        }
+    }
+};
+
 template <typename ArgT>
 __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int sw, int lane)
 {
     const int g = blockIdx.x;
-    const int r0 = g * c.R;
-    const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n, NS = c.NS;
+    const int R = c.R, n = t.n;
     const int NV = c.RB > 0 ? 2 : 1;
-    const double inf = d_inf();
-    const int btm = min(*c.btmax, B1 - 1);
-    const bool halo_on = (g > 0 && btm > 0);  // lower slices push into this one
-    const bool pushes = (g + 1 < c.G);
-    const int lblocks = Kp >> 5;
-    uint32_t cost_phase = 0, scanned_phase = 0, halo_phase = 0;
+    Finisher<ArgT> fin(t, c, sm, sw, c.NS, lane);
+    const int lblocks = fin.lblocks;
+    uint32_t cost_phase = 0, scanned_phase = 0;
     long long pc[3] = {0, 0, 0};  // profile (warp 0): wait for the scan, wait for halo / ring, work
-    long long pcc[2] = {0, 0};    // split of the work: loads + combine, stores
-    long long *pccp = c.prof ? pcc : nullptr;
     long long tp = clock64();
 #define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
     auto wait_costs = [&](long long T) {
@@ -389,65 +467,22 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
     long long T = 0;  // global step: subproblem * n + (n - stage)
     for (int sub = 0; sub < c.nsub; ++sub) {
         const SlotDev sl = c.slots[sub];
-        // ---- terminal stage n (HelpFunctions.jl:27-43) = the rows stage n-1 reads:  P[b][l] = (b == b~_l(n)) ? s_l(n) : Inf
         wait_costs(T);
-        {
-            const double *sn = sm.ss + (size_t)(T % 3) * Kp;
-            const int *bn = sm.bts + (size_t)(T % 3) * Kp;
-            double *Pw = sm.Ps + (size_t)((n - 1) & 1) * R * Kp;
-            // n == 1: only the terminal stage exists, it is the exit state (slot 1 of the reference); n == 2: it is slot 2
-            double *phi = (n == 1) ? sl.phi : (n == 2) ? sl.phi + (size_t)B1 * Kp : nullptr;
-            for (int unit = sw; unit < R * lblocks; unit += NS) {
-                const int row = unit / lblocks, l = ((unit - row * lblocks) << 5) + lane, b = r0 + row;
-                if (l < K && b < B1) {
-                    const double v = (b == bn[l]) ? sn[l] : inf;
-                    Pw[row * Kp + l] = v;
-                    if (phi) phi[(size_t)b * Kp + l] = v;
-                }
-            }
-            for (int v = 0; v < NV; ++v) finished(v);
-        }
+        fin.terminal(sl, T);
+        for (int v = 0; v < NV; ++v) finished(v);
         ++T;
         for (int i = n - 1; i >= 1; --i, ++T) {
             wait_costs(T);
-            FinishArgs a;
-            a.pv = sm.pv;
-            a.pa = sm.pa;
-            a.bt = sm.bts + (size_t)(T % 3) * Kp;
-            a.Pn = sm.Ps + (size_t)((i - 1) & 1) * R * Kp;
-            a.umap = sm.umap;
-            a.hring = c.halo + ((size_t)(T % kHaloRing) * B1 + r0) * Kp;
-            a.phi = (i <= 2) ? sl.phi + ((size_t)((i + 1) & 1) * B1 + r0) * Kp : nullptr;
-            a.argrow = reinterpret_cast<unsigned char *>(sl.arg) + ((size_t)(i - 1) * B1 + r0) * Kp * sizeof(ArgT);
-            a.JS = c.JS; a.R = R; a.Kp = Kp; a.K = K; a.B1 = B1; a.r0 = r0;
             for (int v = 0; v < NV; ++v) {
                 mbar_wait_wd(&sm.mbar[MB_SCANNED + v], (scanned_phase >> v) & 1u, c.err);
                 scanned_phase ^= 1u << v;
                 PROF_LAP(0);
                 if (v == 0) {
-                    // my next rows receive the lower slices' block by TMA (issued by the comm warp): it must have
-                    // landed before my own results overwrite the cells I produce myself
-                    if (halo_on && i >= 2) {
-                        mbar_wait_wd(&sm.mbar[MB_HALO + (i & 1)], (halo_phase >> (i & 1)) & 1u, c.err);
-                        halo_phase ^= 1u << (i & 1);
-                    }
-                    // back-pressure: the successors consumed the ring slot this step overwrites
-                    if (pushes) {
-                        unsigned int spins = 0;
-                        while ((long long)lds_acquire(&sm.mbar[RING_OK]) < T) {
-                            __nanosleep(64);
-                            if ((++spins & 0xfffffu) == 0 && *(volatile int *)&c.err[3]) break;  // the comm warp gave up
-                        }
-                    }
+                    fin.wait_inputs(i, T);
                     PROF_LAP(1);
                 }
                 const int ub = v == 0 ? 0 : c.RA * lblocks, ue = v == 0 ? c.RA * lblocks : R * lblocks;
-                switch (c.JS) {
-                    case 1: finish_rows<1, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
-                    case 2: finish_rows<2, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
-                    case 4: finish_rows<4, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
-                    default: finish_rows<0, ArgT>(a, ub, ue, sw, NS, lane, pccp); break;
-                }
+                fin.rows(sl, i, T, ub, ue);
                 finished(v);
                 PROF_LAP(2);
             }
@@ -455,8 +490,8 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
     }
     if (c.prof && sw == 0 && lane == 0) {
         for (int k = 0; k < 3; ++k) c.prof[(size_t)g * 16 + 5 + k] = pc[k];
-        c.prof[(size_t)g * 16 + 14] = pcc[0];
-        c.prof[(size_t)g * 16 + 15] = pcc[1];
+        c.prof[(size_t)g * 16 + 14] = fin.pcc[0];
+        c.prof[(size_t)g * 16 + 15] = fin.pcc[1];
     }
 #undef PROF_LAP
 }
@@ -484,7 +519,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
 {
     const int g = blockIdx.x;
     const int r0 = g * c.R;
-    const int Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n, NS = c.NS;
+    const int Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n, NF = c.NF;
     const int ncw = (c.JS * c.tpg) >> 5;
     const int btm = min(*c.btmax, B1 - 1);
     const int D = (btm + R - 1) / R;  // slices a push can span
@@ -504,16 +539,21 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         ring_val = kNever;
         if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
     }
+    if (c.decouple) {  // timing experiment only (results are wrong): ignore the neighbours
+        pred_seen = kNever;
+        ring_val = kNever;
+        if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+    }
     unsigned int idle = 0;
-    long long pc[6] = {0, 0, 0, 0, 0, 0};  // profile: loop trips, idle trips, pred polls, succ polls, -, steps
+    long long pc[6] = {0, 0, 0, 0, 0, 0};  // profile: loop trips, idle trips, pred polls, succ polls, SM id, cost rows loaded
 
     for (;;) {
         bool progress = false;
-        const unsigned int fin_cnt = lds_acquire_u32(&sm.mbar[CNT_FINISHED]);  // NS arrivals per finished step
+        const unsigned int fin_cnt = lds_acquire_u32(&sm.mbar[CNT_FINISHED]);  // NF arrivals per finished step
         const unsigned int scn_cnt = lds_acquire_u32(&sm.mbar[CNT_SCANNED]);   // ncw arrivals per scanned stage
         pc[0] += 1;
         // ---- cost cursor --------------------------------------------------------------------------------
-        while (cT < Ttot && (cT < 3 || reached(fin_cnt, (unsigned long long)(cT - 2) * NS))) {
+        while (cT < Ttot && (cT < 3 || reached(fin_cnt, (unsigned long long)(cT - 2) * NF))) {
             if (lane == 0) {
                 const SlotDev &sl = c.slots[csub];
                 const int b = (int)(cT % 3);
@@ -589,8 +629,12 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
             }
         }
     }
-    if (c.prof && lane == 0)
+    if (c.prof && lane == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        pc[4] = smid;  // which SM hosted this slice
         for (int k = 0; k < 6; ++k) c.prof[(size_t)g * 16 + 8 + k] = pc[k];
+    }
 }
 
 // ===================================== PUBLISHER warp ============================================
@@ -607,7 +651,7 @@ __device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c
     for (int sub = 0; sub < c.nsub; ++sub) {
         ++T;  // the terminal stage pushes nothing
         for (int i = n - 1; i >= 1; --i, ++T) {
-            const unsigned long long want = (unsigned long long)(T + 1) * (unsigned)c.NS;
+            const unsigned long long want = (unsigned long long)(T + 1) * (unsigned)c.NF;
             unsigned int spins = 0;
             while (!reached(lds_acquire_u32(&sm.mbar[CNT_FINISHED]), want)) {
                 __nanosleep(200);  // a quiet poll: this warp shares a scheduler with compute warps
@@ -643,7 +687,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         for (int k = 0; k < 5; ++k) mbar_init(&sm.mbar[k], 1);  // cost[3], halo[2]: one arming arrival + tx bytes
         for (int v = 0; v < 2; ++v) {
             mbar_init(&sm.mbar[MB_SCANNED + v], NC >> 5);
-            mbar_init(&sm.mbar[MB_FINISHED + v], c.NS);
+            mbar_init(&sm.mbar[MB_FINISHED + v], c.NF);
         }
         sm.mbar[CNT_SCANNED] = 0;
         sm.mbar[CNT_FINISHED] = 0;
@@ -696,9 +740,27 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     const int rowA = rg * TBA, rowB = c.RA + rg * TBB;
     ArgT *pa = reinterpret_cast<ArgT *>(sm.pa);
 
+    // tiles without a second sub-slice have no scatter warps: the compute warps finish their own stage
+    const bool self_finish = (c.NS == 0);
+    const int cwarp = tid >> 5;
+    Finisher<ArgT> fin(t, c, sm, cwarp, NC >> 5, lane);
+    uint32_t scanned_phase = 0;
+    auto finished = [&]() {
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&sm.mbar[MB_FINISHED]);
+            reds_release_inc(&sm.mbar[CNT_FINISHED]);
+        }
+    };
+
     long long T = 0;
     for (int sub = 0; sub < c.nsub; ++sub) {
+        const SlotDev sl = c.slots[sub];
         wait_costs(T);  // terminal stage: nothing to scan, but every role follows every cost phase
+        if (self_finish) {
+            fin.terminal(sl, T);
+            finished();
+        }
         ++T;
         for (int i = n - 1; i >= 1; --i, ++T) {
             const double *Pc = sm.Ps + (size_t)(i & 1) * R * Kp;
@@ -724,11 +786,24 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 PROF_LAP(1);
                 scanned(1);
                 PROF_LAP(2);
+            } else if (self_finish) {
+                // ---- phase C by the compute warps: all partial minima are in shared memory once every warp scanned
+                mbar_wait_wd(&sm.mbar[MB_SCANNED], scanned_phase, c.err);
+                scanned_phase ^= 1u;
+                fin.wait_inputs(i, T);
+                PROF_LAP(2);
+                fin.rows(sl, i, T, 0, R * fin.lblocks);
+                finished();
+                PROF_LAP(3);
             }
             pc[4] += 1;
         }
         // drain: stage 1 (or the terminal stage when n == 1) is finished; keeps the barrier phases aligned
         for (int v = 0; v < NV; ++v) wait_finished(v);
+    }
+    if (c.prof && tid == 0 && self_finish) {
+        c.prof[(size_t)g * 16 + 14] = fin.pcc[0];
+        c.prof[(size_t)g * 16 + 15] = fin.pcc[1];
     }
     if (c.prof && tid == 0) {
         c.prof[(size_t)g * 16 + 0] = pc[0];
@@ -742,10 +817,19 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 
 // ---- host side -----------------------------------------------------------------------------------
 struct Variant { int TBA, TBB, TL; };
-// (rows of sub-slice A, rows of sub-slice B, levels) per thread tile.  Every variant is built for CTAs of up to 512
-// threads (128 registers per thread: no spills, and room for the scatter warps that hide phase C).
-static const Variant kVariants[] = {{4, 3, 2}, {4, 4, 2}, {3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 1, 2}, {1, 1, 2},
-                                    {1, 0, 2}, {4, 4, 1}, {3, 3, 1}, {2, 2, 1}, {1, 1, 1}, {1, 0, 1}};
+// (rows of sub-slice A, rows of sub-slice B, levels) per thread tile.  TBB = 0: one sub-slice; phase C then runs
+// after the scan, either on the compute warps themselves (NS = 0) or on scatter warps.  Every variant is built for
+// CTAs of up to 512 threads (128 registers per thread, no spills).
+#define BB200_VARIANTS(X)                                                                                      \
+    X(0, 7, 0, 2) X(1, 8, 0, 2) X(2, 6, 0, 2) X(3, 5, 0, 2) X(4, 4, 0, 2) X(5, 3, 0, 2) X(6, 2, 0, 2) X(7, 1, 0, 2) \
+    X(8, 8, 0, 1) X(9, 4, 0, 1) X(10, 2, 0, 1) X(11, 1, 0, 1)                                                    \
+    X(12, 4, 3, 2) X(13, 4, 4, 2) X(14, 3, 3, 2) X(15, 3, 2, 2) X(16, 2, 2, 2) X(17, 2, 1, 2) X(18, 1, 1, 2)     \
+    X(19, 4, 4, 1) X(20, 2, 2, 1) X(21, 1, 1, 1)
+static const Variant kVariants[] = {
+#define X(idx, a, b, l) {a, b, l},
+    BB200_VARIANTS(X)
+#undef X
+};
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kWaveThreads = kWaveThreadsSmall;
 
@@ -767,7 +851,8 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int N
     c.jper = ((t.K + JS - 1) / JS + 1) & ~1;  // even: successors are taken in aligned pairs
     c.tpg = ((c.RG * c.nLG + 31) / 32) * 32;
     c.NS = NS;
-    c.threads = c.JS * c.tpg + 64 + 32 * NS;  // + comm warp + publisher warp + scatter warps
+    c.NF = c.NS > 0 ? c.NS : c.JS * c.tpg / 32;  // warps that finish a stage: scatter warps, else the compute warps
+    c.threads = c.JS * c.tpg + 64 + 32 * c.NS;  // + comm warp + publisher warp + scatter warps
     c.smem = carve(t, c, argw, nullptr, nullptr);
 }
 
@@ -775,9 +860,9 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     int want_variant, WaveCfg &cfg)
 {
     if (t.M > kMaxM || argw != 1) return false;  // K > 255: the jump-cost table would not fit in shared memory anyway
-    const int want_ns = want_variant / 100;
+    const int want_ns = want_variant / 100;  // 0: automatic, 1..8: that many scatter warps, 10: none (NS = 0)
     want_variant %= 100;
-    static const int kNsChoices[] = {1, 2, 3, 4, 6, 8};
+    static const int kNsChoices[] = {0, 1, 2, 3, 4, 6, 8};
     double best_stage = -1.;
     bool found = false;
     for (int v = 0; v < kNumVariants; ++v) {
@@ -786,9 +871,10 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
         for (int js = 1; js <= 16; ++js) {
             if (want_js > 0 && js != want_js) continue;
             if (js > t.K) break;
-            for (int nsi = 0; nsi < 6; ++nsi) {
+            for (int nsi = 0; nsi < 7; ++nsi) {
                 const int ns = kNsChoices[nsi];
-                if (want_ns > 0 && ns != want_ns) continue;
+                if (kVariants[v].TBB > 0 && ns == 0) continue;  // two sub-slices need scatter warps
+                if (want_ns > 0 && ns != want_ns % 10) continue;  // 100 * NS forces NS scatter warps, 1000: none
                 int gmax = want_ctas > 0 ? want_ctas : num_sms;
                 if (gmax > num_sms) gmax = num_sms;
                 WaveCfg c = cfg;
@@ -806,27 +892,32 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 // sub-slice that hides it.
                 const int cwarps = c.JS * c.tpg / 32;
                 const int sched = (cwarps + 3) / 4;
-                const double stall = sched == 1 ? 1.5 : sched == 2 ? 1.3 : 1.2;  // fewer warps hide less latency
+                // one warp per scheduler cannot hide the compare -> select latency; three or more run with 128
+                // registers and a longer schedule (measured: 1.5 / 1.3 / 1.4)
+                const double stall = sched == 1 ? 1.5 : sched == 2 ? 1.3 : 1.4;
                 auto scan = [&](int tb) {
                     if (tb == 0) return 0.0;
                     const double per_j = 7.0 * tb * c.TL + 2.0 * c.TL + ((tb + 1) / 2) + ((c.TL + 1) / 2) + 3.0;
                     return per_j * c.jper * sched * stall + 150.0;
                 };
-                // a batch of four units per scatter warp; the scatter warps only get the issue slots the scan leaves
+                // phase C is latency bound: time per unit (32 cells) and finisher warp; warps that share the SM with the
+                // scan only get the issue slots it leaves
                 auto finish = [&](int rows, bool hidden) {
                     const int units = rows * (t.Kp / 32);
-                    const int batches = (units + ns * 4 - 1) / (ns * 4);
-                    return batches * (hidden ? 1200.0 + 450.0 * js : 450.0 + 120.0 * js) + 150.0;
+                    const int per_warp = (units + c.NF - 1) / c.NF;
+                    const double generic = (js == 1 || js == 2 || js == 4) ? 1.0 : 2.0;  // other splits: rolled combine loop
+                    return per_warp * generic * (hidden ? 300.0 + 110.0 * js : 150.0 + 60.0 * js) + 300.0;
                 };
                 const double sa = scan(c.TB), sb = scan(c.TBB);
                 double stage;
                 if (c.TBB > 0) {
                     const double fa = finish(c.RA, true), fb = finish(c.RB, true);
-                    stage = sa + sb + (fa > sb ? fa - sb : 0.) + (fb > sa ? fb - sa : 0.);
+                    // a shorter finish also shortens the lag a successor slice needs behind this one
+                    stage = sa + sb + (fa > sb ? fa - sb : 0.) + (fb > sa ? fb - sa : 0.) + 0.15 * (fa + fb);
                 } else {
-                    stage = sa + finish(c.RA, false);
+                    stage = sa + finish(c.RA, false) + (ns == 0 ? 800.0 : 300.0);  // + the hand-over after the scan
                 }
-                stage += 25.0 * ns;  // scatter warps take issue slots from the scan
+                stage += 10.0 * c.NS;  // scatter warps take issue slots from the scan
                 if (!found || stage < best_stage) {
                     best_stage = stage;
                     cfg = c;
@@ -853,19 +944,9 @@ cudaError_t launch_wavefront(const Tables &t, const WaveCfg &cfg, int argw, cuda
 {
     if (argw != 1) return cudaErrorInvalidValue;
     switch (cfg.variant) {
-        case 0: return launch_variant<4, 3, 2>(t, cfg, st);
-        case 1: return launch_variant<4, 4, 2>(t, cfg, st);
-        case 2: return launch_variant<3, 3, 2>(t, cfg, st);
-        case 3: return launch_variant<3, 2, 2>(t, cfg, st);
-        case 4: return launch_variant<2, 2, 2>(t, cfg, st);
-        case 5: return launch_variant<2, 1, 2>(t, cfg, st);
-        case 6: return launch_variant<1, 1, 2>(t, cfg, st);
-        case 7: return launch_variant<1, 0, 2>(t, cfg, st);
-        case 8: return launch_variant<4, 4, 1>(t, cfg, st);
-        case 9: return launch_variant<3, 3, 1>(t, cfg, st);
-        case 10: return launch_variant<2, 2, 1>(t, cfg, st);
-        case 11: return launch_variant<1, 1, 1>(t, cfg, st);
-        case 12: return launch_variant<1, 0, 1>(t, cfg, st);
+#define X(idx, a, b, l) case idx: return launch_variant<a, b, l>(t, cfg, st);
+        BB200_VARIANTS(X)
+#undef X
         default: return cudaErrorInvalidValue;
     }
 }

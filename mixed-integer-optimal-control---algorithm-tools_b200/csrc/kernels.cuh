@@ -27,7 +27,8 @@ struct WaveCfg {
     int JS;       // j-split: thread groups scanning disjoint successor ranges
     int jper;     // successors per group = ceil(K / JS), rounded up to even
     int tpg;      // threads per group (multiple of 32)
-    int NS;       // scatter warps (phase C)
+    int NS;       // scatter warps (phase C); 0 when the tile has one sub-slice and the compute warps finish it
+    int NF;       // warps that finish a stage: NS, or the compute warps
     int threads;  // JS * tpg compute threads + comm warp + publisher warp + NS scatter warps
     size_t smem;  // dynamic shared memory bytes
     int nsub;     // subproblems walked by this launch
@@ -37,6 +38,7 @@ struct WaveCfg {
     int *err;                    // [4]: inexact, stale, watchdog, abort
     const int *btmax;
     long long *prof;             // optional [G][16] cycle counters (NULL = off)
+    int decouple;                // timing experiments only: CTAs ignore their neighbours (wrong results)
 };
 
 // Fills the geometry fields of cfg for the given tables; returns false when the shape cannot run on the

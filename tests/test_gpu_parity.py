@@ -128,11 +128,14 @@ def test_synthetic_config4_shape_vs_oracle(gpu_lib, oracle, tie):
     assert st["ctas"] >= 100  # the pipelined path really spreads over the GPU
 
 
-@pytest.mark.parametrize("tune", [dict(ctas=8, jsplit=1), dict(ctas=20, jsplit=2), dict(ctas=16, jsplit=3, variant=2),
-                                  dict(ctas=40, jsplit=3, variant=4), dict(ctas=148, jsplit=6, variant=1),
-                                  dict(jsplit=1, variant=6), dict(ctas=9, variant=3), dict(variant=5),
-                                  dict(variant=107), dict(variant=408), dict(ctas=30, variant=9), dict(variant=10),
-                                  dict(variant=311), dict(variant=12), dict(variant=413, jsplit=2)])
+@pytest.mark.parametrize("tune", [dict(ctas=8, jsplit=1), dict(ctas=20, jsplit=2), dict(variant=1), dict(ctas=20, variant=2),
+                                  dict(variant=3), dict(variant=4, jsplit=3), dict(ctas=148, jsplit=6, variant=5),
+                                  dict(variant=6), dict(variant=7, jsplit=1), dict(variant=8), dict(ctas=9, variant=9),
+                                  dict(variant=10), dict(variant=11), dict(variant=12, jsplit=2), dict(variant=113),
+                                  dict(variant=213, jsplit=3), dict(variant=413), dict(ctas=16, variant=214),
+                                  dict(variant=115), dict(variant=316), dict(variant=617), dict(variant=218),
+                                  dict(variant=119), dict(ctas=30, variant=220), dict(variant=321),
+                                  dict(variant=822, jsplit=2)])
 def test_wavefront_geometries(gpu_lib, oracle, tune):
     """Every tile variant / CTA count / j-split / scatter-warp count (variant + 100 * NS) of the pipelined kernel
     gives identical bits."""

@@ -36,3 +36,5 @@ for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
     if 0 <= gsel < G:
         print(f"cta {gsel:3d} " + line(prof[gsel]))
 print("avg     " + line(prof[:G].mean(axis=0)))
+if os.environ.get("PROFILE_DUMP"):
+    np.save(os.environ["PROFILE_DUMP"], prof[:G])
