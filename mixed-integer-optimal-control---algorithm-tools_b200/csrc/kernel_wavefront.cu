@@ -306,6 +306,9 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
             ok[u] = in_tab && row + bt < rows_left;
         }
         if constexpr (JSC > 0) {
+            // all partial (min, argmin) pairs are loaded before the first compare; tournament in ascending group order,
+            // on ties the earlier group stays (strict '>', HelpFunctions.jl:73).  Partial minima are never NaN and
+            // carry MARK with +Inf, so this equals the sequential scan.
             double v[CU][JSC];
             int g[CU][JSC];
 #pragma unroll
@@ -315,8 +318,6 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
                     v[u][q] = pv[q * RK + x_[u]];
                     g[u][q] = (int)pa[q * RK + x_[u]];
                 }
-            // tournament in ascending group order; on ties the earlier group stays (strict '>', HelpFunctions.jl:73).
-            // Partial minima are never NaN and carry MARK with +Inf, so this equals the sequential scan.
 #pragma unroll
             for (int w = 1; w < JSC; w *= 2)
 #pragma unroll
@@ -327,14 +328,32 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
 #pragma unroll
             for (int u = 0; u < CU; ++u) { val[u] = v[u][0]; arg[u] = g[u][0]; }
         } else {
+            // any other split: sequential scan over the groups, two per trip (both loaded before either is compared)
 #pragma unroll
             for (int u = 0; u < CU; ++u) { val[u] = inf; arg[u] = MARKI; }
-            for (int q = 0; q < a.JS; ++q) {
+            int q = 0;
+#pragma unroll 1
+            for (; q + 1 < a.JS; q += 2) {
+                double v0[CU], v1[CU];
+                int g0[CU], g1[CU];
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    const int xx = q * RK + x_[u];
+                    v0[u] = pv[xx]; g0[u] = (int)pa[xx];
+                    v1[u] = pv[xx + RK]; g1[u] = (int)pa[xx + RK];
+                }
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    if (v0[u] > v1[u]) { v0[u] = v1[u]; g0[u] = g1[u]; }
+                    if (val[u] > v0[u]) { val[u] = v0[u]; arg[u] = g0[u]; }
+                }
+            }
+            if (q < a.JS) {
 #pragma unroll
                 for (int u = 0; u < CU; ++u) {
                     const double v = pv[q * RK + x_[u]];
                     const int g = (int)pa[q * RK + x_[u]];
-                    if (val[u] > v) { val[u] = v; arg[u] = g; }  // strict: earliest group wins ties
+                    if (val[u] > v) { val[u] = v; arg[u] = g; }
                 }
             }
         }
@@ -431,7 +450,6 @@ struct Finisher {
         a.JS = c.JS; a.R = R; a.Kp = Kp; a.K = t.K; a.B1 = B1; a.r0 = r0;
         long long *pccp = c.prof ? pcc : nullptr;
         switch (c.JS) {
-            case 1: finish_rows<1, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
             case 2: finish_rows<2, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
             case 4: finish_rows<4, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
             default: finish_rows<0, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
@@ -573,6 +591,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
             const long long hT = (long long)hsub * n + hk;
             if (pred_seen < hT) {
                 long long m = kNever;
+#pragma unroll 1
                 for (int idx = lane; idx < npred; idx += 32)
                     m = min(m, (long long)ld_acquire(c.flags + (size_t)(g - idx - 1) * kFlagStride));
                 pred_seen = max(pred_seen, warp_min(m));
@@ -599,6 +618,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         // scatter warps work on step >= cT - 3 at most cT: keep the ring bound a few steps ahead of them
         if (ring_val < Ttot && ring_val < cT + 2) {
             long long m = kNever;
+#pragma unroll 1
             for (int idx = lane; idx < nsucc; idx += 32)
                 m = min(m, (long long)ld_acquire(c.flags + (size_t)(g + idx + 1) * kFlagStride));
             m = warp_min(m);
@@ -741,7 +761,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     ArgT *pa = reinterpret_cast<ArgT *>(sm.pa);
 
     // tiles without a second sub-slice have no scatter warps: the compute warps finish their own stage
-    const bool self_finish = (c.NS == 0);
+    const bool self_finish = (TBB == 0) && (c.NS == 0);  // two sub-slices always have scatter warps
     const int cwarp = tid >> 5;
     Finisher<ArgT> fin(t, c, sm, cwarp, NC >> 5, lane);
     uint32_t scanned_phase = 0;
@@ -824,7 +844,7 @@ struct Variant { int TBA, TBB, TL; };
     X(0, 7, 0, 2) X(1, 8, 0, 2) X(2, 6, 0, 2) X(3, 5, 0, 2) X(4, 4, 0, 2) X(5, 3, 0, 2) X(6, 2, 0, 2) X(7, 1, 0, 2) \
     X(8, 8, 0, 1) X(9, 4, 0, 1) X(10, 2, 0, 1) X(11, 1, 0, 1)                                                    \
     X(12, 4, 3, 2) X(13, 4, 4, 2) X(14, 3, 3, 2) X(15, 3, 2, 2) X(16, 2, 2, 2) X(17, 2, 1, 2) X(18, 1, 1, 2)     \
-    X(19, 4, 4, 1) X(20, 2, 2, 1) X(21, 1, 1, 1)
+    X(19, 4, 4, 1) X(20, 2, 2, 1) X(21, 1, 1, 1) X(22, 4, 3, 1) X(23, 3, 3, 1)
 static const Variant kVariants[] = {
 #define X(idx, a, b, l) {a, b, l},
     BB200_VARIANTS(X)
@@ -905,7 +925,7 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 auto finish = [&](int rows, bool hidden) {
                     const int units = rows * (t.Kp / 32);
                     const int per_warp = (units + c.NF - 1) / c.NF;
-                    const double generic = (js == 1 || js == 2 || js == 4) ? 1.0 : 2.0;  // other splits: rolled combine loop
+                    const double generic = (js <= 2 || js == 4) ? 1.0 : 1.5;  // other splits: rolled combine loop
                     return per_warp * generic * (hidden ? 300.0 + 110.0 * js : 150.0 + 60.0 * js) + 300.0;
                 };
                 const double sa = scan(c.TB), sb = scan(c.TBB);

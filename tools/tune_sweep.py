@@ -19,7 +19,7 @@ inst = wl.synthetic(n=n, B=999, seed=20251018) if kind == "synthetic" else wl.ex
 plan = m.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt, flags=4)
 plan.upload(0, inst.df, inst.u_old)
 TILES = ["7+0x2", "8+0x2", "6+0x2", "5+0x2", "4+0x2", "3+0x2", "2+0x2", "1+0x2", "8+0x1", "4+0x1", "2+0x1", "1+0x1",
-         "4+3x2", "4+4x2", "3+3x2", "3+2x2", "2+2x2", "2+1x2", "1+1x2", "4+4x1", "2+2x1", "1+1x1"]
+         "4+3x2", "4+4x2", "3+3x2", "3+2x2", "2+2x2", "2+1x2", "1+1x2", "4+4x1", "2+2x1", "1+1x1", "4+3x1", "3+3x1"]
 
 
 def run(ctas, js, code):
