@@ -130,7 +130,7 @@ struct Smem {
     double *cs;       // [K*Kp]    jump costs
     double *pv;       // [JS*R*Kp] partial minima of the j-groups
     unsigned char *pa;  // ArgT[JS*R*Kp] partial argmins
-    int *umap;        // [R*Kp/32] phase-C work unit -> (row << 16) | first level
+    int *umap;        // [R*ceil(Kp/64)] phase-C work unit -> (row << 16) | first level
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -258,7 +258,7 @@ struct FinishArgs {
     const double *pv;
     const unsigned char *pa;  // ArgT[]
     const int *bt;            // budget use of this stage's levels
-    const int *umap;          // work unit -> (row << 16) | first level, see scatter_warp
+    const int *umap;          // work unit (64 levels of one row) -> (row << 16) | first level
     double *Pn;               // rows of the next stage, [R][Kp]
     double *hring;            // ring slot of this step at row r0, [B1 - r0][Kp]
     double *phi;              // exit slot that receives this stage's values (i <= 2) at row r0, or nullptr
@@ -266,109 +266,122 @@ struct FinishArgs {
     int JS, R, Kp, K, B1, r0;
 };
 
-// Finishes the cells of `CU` work units at once (a unit = 32 consecutive levels of one source row, one cell per
-// lane) so that the dependent load -> compare -> select chains of different cells overlap.  Units [ub, ue) of the
-// CTA belong to the sub-slice being finished; warp sw of NS takes every NS-th one.
+// Finishes `CU` work units at once so that the dependent load -> compare -> select chains of different cells
+// overlap.  A unit is 64 consecutive levels of one source row; a lane owns two neighbouring cells and fetches
+// their partial minima with one 16-byte load per j-group (and both argmins with one 2-byte load).  Units [ub, ue)
+// of the CTA belong to the sub-slice being finished; warp sw of NS takes every NS-th one.
 template <int JSC, typename ArgT>
 __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue, int sw, int NS, int lane, long long *pcc)
 {
+    static_assert(sizeof(ArgT) == 1, "the packed two-cell argmin load assumes one byte per cell");
     long long tq0 = pcc ? clock64() : 0;
-    constexpr int CU = 4;
-    constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
+    constexpr int CU = 2;
     const double inf = d_inf();
     const double *__restrict__ pv = a.pv;
-    const ArgT *__restrict__ pa = reinterpret_cast<const ArgT *>(a.pa);
+    const unsigned char *__restrict__ pa = a.pa;
     const int *__restrict__ btp = a.bt;
     const int *__restrict__ umap = a.umap;
-    ArgT *__restrict__ argrow = reinterpret_cast<ArgT *>(a.argrow);
+    unsigned char *__restrict__ argrow = a.argrow;
     double *__restrict__ Pn = a.Pn;
     double *__restrict__ hring = a.hring;
     const int RK = a.R * a.Kp;
     const int rows_left = a.B1 - a.r0;  // rows of this slice that exist in the table
     for (int u0 = ub + sw; u0 < ue; u0 += NS * CU) {
-        double val[CU];
-        int arg[CU], x_[CU], y_[CU];
-        bool no_src[CU], ok[CU];
+        double val[CU][2];
+        int arg[CU][2], x_[CU], y_[CU][2];
+        bool no_src[CU][2], ok[CU][2];
 #pragma unroll
         for (int u = 0; u < CU; ++u) {
             const int unit = u0 + u * NS;
             const bool live = unit < ue;
             const int m = umap[live ? unit : ub];
-            const int row = m >> 16, l = (m & 0xffff) + lane;
-            const int bt = btp[l];
-            const bool in_tab = live && l < a.K && row < rows_left;
-            x_[u] = row * a.Kp + l;
-            y_[u] = x_[u] + bt * a.Kp;  // (target row - r0) * Kp + l
-            // target cell (bsrc, l) of my rows has no source row when bsrc < b~_l: +Inf (:47).  This also covers
-            // levels that are unreachable at this stage (b~ clamped to B1).
-            no_src[u] = in_tab && a.r0 + row < bt;
-            // cells outside `for b = 0:B-b~` (:69) are not computed by the reference either
-            ok[u] = in_tab && row + bt < rows_left;
+            const int row = m >> 16;
+            const int l0 = min((m & 0xffff) + 2 * lane, a.Kp - 2);  // a half-filled last unit re-reads the last pair
+            const bool lane_live = live && (m & 0xffff) + 2 * lane < a.Kp;
+            const int2 bt = *reinterpret_cast<const int2 *>(btp + l0);
+            x_[u] = row * a.Kp + l0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int bte = e ? bt.y : bt.x;
+                const bool in_tab = lane_live && l0 + e < a.K && row < rows_left;
+                y_[u][e] = x_[u] + e + bte * a.Kp;  // (target row - r0) * Kp + l
+                // target cell (bsrc, l) of my rows has no source row when bsrc < b~_l: +Inf (:47).  This also covers
+                // levels that are unreachable at this stage (b~ clamped to B1).
+                no_src[u][e] = in_tab && a.r0 + row < bte;
+                // cells outside `for b = 0:B-b~` (:69) are not computed by the reference either
+                ok[u][e] = in_tab && row + bte < rows_left;
+            }
         }
         if constexpr (JSC > 0) {
             // all partial (min, argmin) pairs are loaded before the first compare; tournament in ascending group order,
             // on ties the earlier group stays (strict '>', HelpFunctions.jl:73).  Partial minima are never NaN and
             // carry MARK with +Inf, so this equals the sequential scan.
-            double v[CU][JSC];
-            int g[CU][JSC];
+            double v[CU][JSC][2];
+            int g[CU][JSC];  // both cells' argmins, packed
 #pragma unroll
             for (int u = 0; u < CU; ++u)
 #pragma unroll
                 for (int q = 0; q < JSC; ++q) {
-                    v[u][q] = pv[q * RK + x_[u]];
-                    g[u][q] = (int)pa[q * RK + x_[u]];
+                    const double2 w = *reinterpret_cast<const double2 *>(pv + q * RK + x_[u]);
+                    v[u][q][0] = w.x;
+                    v[u][q][1] = w.y;
+                    g[u][q] = (int)*reinterpret_cast<const unsigned short *>(pa + q * RK + x_[u]);
                 }
+            int gw[CU][JSC][2];
+#pragma unroll
+            for (int u = 0; u < CU; ++u)
+#pragma unroll
+                for (int q = 0; q < JSC; ++q) { gw[u][q][0] = g[u][q]; gw[u][q][1] = g[u][q]; }
 #pragma unroll
             for (int w = 1; w < JSC; w *= 2)
 #pragma unroll
                 for (int q = 0; q + w < JSC; q += 2 * w)
 #pragma unroll
                     for (int u = 0; u < CU; ++u)
-                        if (v[u][q] > v[u][q + w]) { v[u][q] = v[u][q + w]; g[u][q] = g[u][q + w]; }
 #pragma unroll
-            for (int u = 0; u < CU; ++u) { val[u] = v[u][0]; arg[u] = g[u][0]; }
+                        for (int e = 0; e < 2; ++e)
+                            if (v[u][q][e] > v[u][q + w][e]) { v[u][q][e] = v[u][q + w][e]; gw[u][q][e] = gw[u][q + w][e]; }
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                val[u][0] = v[u][0][0];
+                val[u][1] = v[u][0][1];
+                arg[u][0] = gw[u][0][0] & 0xff;
+                arg[u][1] = gw[u][0][1] >> 8;
+            }
         } else {
-            // any other split: sequential scan over the groups, two per trip (both loaded before either is compared)
+            // any other split: sequential scan over the groups
+            int gw[CU][2];
 #pragma unroll
-            for (int u = 0; u < CU; ++u) { val[u] = inf; arg[u] = MARKI; }
-            int q = 0;
+            for (int u = 0; u < CU; ++u) { val[u][0] = inf; val[u][1] = inf; gw[u][0] = 0xffff; gw[u][1] = 0xffff; }
 #pragma unroll 1
-            for (; q + 1 < a.JS; q += 2) {
-                double v0[CU], v1[CU];
-                int g0[CU], g1[CU];
+            for (int q = 0; q < a.JS; ++q) {
 #pragma unroll
                 for (int u = 0; u < CU; ++u) {
-                    const int xx = q * RK + x_[u];
-                    v0[u] = pv[xx]; g0[u] = (int)pa[xx];
-                    v1[u] = pv[xx + RK]; g1[u] = (int)pa[xx + RK];
-                }
-#pragma unroll
-                for (int u = 0; u < CU; ++u) {
-                    if (v0[u] > v1[u]) { v0[u] = v1[u]; g0[u] = g1[u]; }
-                    if (val[u] > v0[u]) { val[u] = v0[u]; arg[u] = g0[u]; }
+                    const double2 w = *reinterpret_cast<const double2 *>(pv + q * RK + x_[u]);
+                    const int g = (int)*reinterpret_cast<const unsigned short *>(pa + q * RK + x_[u]);
+                    if (val[u][0] > w.x) { val[u][0] = w.x; gw[u][0] = g; }  // strict: earliest group wins ties
+                    if (val[u][1] > w.y) { val[u][1] = w.y; gw[u][1] = g; }
                 }
             }
-            if (q < a.JS) {
 #pragma unroll
-                for (int u = 0; u < CU; ++u) {
-                    const double v = pv[q * RK + x_[u]];
-                    const int g = (int)pa[q * RK + x_[u]];
-                    if (val[u] > v) { val[u] = v; arg[u] = g; }
-                }
-            }
+            for (int u = 0; u < CU; ++u) { arg[u][0] = gw[u][0] & 0xff; arg[u][1] = gw[u][1] >> 8; }
         }
         if (pcc) { const long long tq = clock64(); pcc[0] += tq - tq0; tq0 = tq; }
 #pragma unroll
-        for (int u = 0; u < CU; ++u) {
-            if (no_src[u]) Pn[x_[u]] = inf;
-            if (ok[u]) argrow[x_[u]] = (ArgT)arg[u];
-            if (ok[u] && y_[u] < RK) Pn[y_[u]] = val[u];
-            if (ok[u] && y_[u] >= RK) hring[y_[u]] = val[u];
-        }
+        for (int u = 0; u < CU; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (no_src[u][e]) Pn[x_[u] + e] = inf;
+                if (ok[u][e]) argrow[x_[u] + e] = (unsigned char)arg[u][e];
+                if (ok[u][e] && y_[u][e] < RK) Pn[y_[u][e]] = val[u][e];
+                if (ok[u][e] && y_[u][e] >= RK) hring[y_[u][e]] = val[u][e];
+            }
         if (a.phi) {  // stages 2 and 1 are the exit state (S7)
 #pragma unroll
             for (int u = 0; u < CU; ++u)
-                if (ok[u]) a.phi[y_[u]] = val[u];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (ok[u][e]) a.phi[y_[u][e]] = val[u][e];
         }
         if (pcc) { const long long tq = clock64(); pcc[1] += tq - tq0; tq0 = tq; }
     }
@@ -382,13 +395,14 @@ struct Finisher {
     const WaveCfg &c;
     const Smem &sm;
     const int fw, NF, lane;  // this warp's index among the NF finisher warps
-    const int r0, lblocks;
+    const int r0, lblocks;  // 32-level blocks per row (terminal stage)
+    const int ublocks;      // 64-level work units per row (phase C)
     bool halo_on, pushes;
     uint32_t halo_phase = 0;
     long long pcc[2] = {0, 0};  // profile: loads + combine, stores
 
     __device__ __forceinline__ Finisher(const Tables &t_, const WaveCfg &c_, const Smem &sm_, int fw_, int NF_, int lane_)
-        : t(t_), c(c_), sm(sm_), fw(fw_), NF(NF_), lane(lane_), r0(blockIdx.x * c_.R), lblocks(t_.Kp >> 5)
+        : t(t_), c(c_), sm(sm_), fw(fw_), NF(NF_), lane(lane_), r0(blockIdx.x * c_.R), lblocks(t_.Kp >> 5), ublocks((t_.Kp + 63) >> 6)
     {
         const int btm = min(*c.btmax, t.B1 - 1);
         halo_on = (blockIdx.x > 0 && btm > 0);  // lower slices push into this one
@@ -464,7 +478,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
     const int R = c.R, n = t.n;
     const int NV = c.RB > 0 ? 2 : 1;
     Finisher<ArgT> fin(t, c, sm, sw, c.NS, lane);
-    const int lblocks = fin.lblocks;
+    const int ublocks = fin.ublocks;
     uint32_t cost_phase = 0, scanned_phase = 0;
     long long pc[3] = {0, 0, 0};  // profile (warp 0): wait for the scan, wait for halo / ring, work
     long long tp = clock64();
@@ -499,7 +513,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
                     fin.wait_inputs(i, T);
                     PROF_LAP(1);
                 }
-                const int ub = v == 0 ? 0 : c.RA * lblocks, ue = v == 0 ? c.RA * lblocks : R * lblocks;
+                const int ub = v == 0 ? 0 : c.RA * ublocks, ue = v == 0 ? c.RA * ublocks : R * ublocks;
                 fin.rows(sl, i, T, ub, ue);
                 finished(v);
                 PROF_LAP(2);
@@ -702,7 +716,8 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     // one-time: jump costs into shared memory, value rows to +Inf, barriers and counters
     for (int x = tid; x < K * Kp; x += blockDim.x) sm.cs[x] = t.cost[x];
     for (int x = tid; x < 2 * R * Kp; x += blockDim.x) sm.Ps[x] = inf;
-    for (int x = tid; x < R * (Kp >> 5); x += blockDim.x) sm.umap[x] = ((x / (Kp >> 5)) << 16) | ((x % (Kp >> 5)) << 5);
+    for (int x = tid; x < R * ((Kp + 63) >> 6); x += blockDim.x)
+        sm.umap[x] = ((x / ((Kp + 63) >> 6)) << 16) | ((x % ((Kp + 63) >> 6)) << 6);
     if (tid == 0) {
         for (int k = 0; k < 5; ++k) mbar_init(&sm.mbar[k], 1);  // cost[3], halo[2]: one arming arrival + tx bytes
         for (int v = 0; v < 2; ++v) {
@@ -812,7 +827,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 scanned_phase ^= 1u;
                 fin.wait_inputs(i, T);
                 PROF_LAP(2);
-                fin.rows(sl, i, T, 0, R * fin.lblocks);
+                fin.rows(sl, i, T, 0, R * fin.ublocks);
                 finished();
                 PROF_LAP(3);
             }
@@ -923,10 +938,10 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 // phase C is latency bound: time per unit (32 cells) and finisher warp; warps that share the SM with the
                 // scan only get the issue slots it leaves
                 auto finish = [&](int rows, bool hidden) {
-                    const int units = rows * (t.Kp / 32);
+                    const int units = rows * ((t.Kp + 63) / 64);
                     const int per_warp = (units + c.NF - 1) / c.NF;
-                    const double generic = (js <= 2 || js == 4) ? 1.0 : 1.5;  // other splits: rolled combine loop
-                    return per_warp * generic * (hidden ? 300.0 + 110.0 * js : 150.0 + 60.0 * js) + 300.0;
+                    const double generic = (js == 2 || js == 4) ? 1.0 : 1.5;  // other splits: rolled combine loop
+                    return per_warp * generic * (hidden ? 400.0 + 150.0 * js : 200.0 + 80.0 * js) + 300.0;
                 };
                 const double sa = scan(c.TB), sb = scan(c.TBB);
                 double stage;
