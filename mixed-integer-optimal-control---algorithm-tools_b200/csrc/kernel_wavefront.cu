@@ -108,6 +108,19 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
     }
 }
 
+#ifndef BB_COMM_SLEEP
+#define BB_COMM_SLEEP 64
+#endif
+#ifndef BB_PUB_SLEEP
+#define BB_PUB_SLEEP 200
+#endif
+#ifndef BB_UNROLL
+#define BB_UNROLL 4
+#endif
+#ifndef BB_CU
+#define BB_CU 2
+#endif
+constexpr int kUnrollB = BB_UNROLL;  // successor pairs per trip of the phase-B loop
 constexpr long long kNever = (long long)1 << 62;
 
 // shared-memory synchronisation words
@@ -188,7 +201,7 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
     for (int q = 0; q < TL; ++q) s[q] = srow[q];
     // main loop: full pairs, one straight-line block so that the two candidates' chains interleave
     const int je2 = jb + ((je - jb) & ~1);
-#pragma unroll 4
+#pragma unroll kUnrollB
     for (int j = jb; j < je2; j += 2) {
         double p0[TB], p1[TB];
 #pragma unroll
@@ -275,7 +288,7 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
 {
     static_assert(sizeof(ArgT) == 1, "the packed two-cell argmin load assumes one byte per cell");
     long long tq0 = pcc ? clock64() : 0;
-    constexpr int CU = 2;
+    constexpr int CU = BB_CU;
     const double inf = d_inf();
     const double *__restrict__ pv = a.pv;
     const unsigned char *__restrict__ pa = a.pa;
@@ -647,7 +660,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         }
         if (cT >= Ttot && !h_active && ring_val >= Ttot) break;
         if (progress) { idle = 0; continue; }
-        __nanosleep(64);
+        __nanosleep(BB_COMM_SLEEP);
         pc[1] += 1;
         if ((++idle & 0x3ffu) == 0) {
             bool abort_now = *(volatile int *)&c.err[3] != 0;
@@ -688,7 +701,7 @@ __device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c
             const unsigned long long want = (unsigned long long)(T + 1) * (unsigned)c.NF;
             unsigned int spins = 0;
             while (!reached(lds_acquire_u32(&sm.mbar[CNT_FINISHED]), want)) {
-                __nanosleep(200);  // a quiet poll: this warp shares a scheduler with compute warps
+                __nanosleep(BB_PUB_SLEEP);  // a quiet poll: this warp shares a scheduler with compute warps
                 if ((++spins & 0xffffu) == 0 && *(volatile int *)&c.err[3] && spins > (1u << 22)) return;  // stuck after an abort
             }
             fence_gpu();
