@@ -145,6 +145,19 @@ def test_wavefront_geometries(gpu_lib, oracle, tune):
                          inst.p, inst.dt, 0, tune=tune)
 
 
+@pytest.mark.parametrize("levels,M,B,tune", [(9, 2, 150, None), (9, 2, 150, dict(variant=413, jsplit=4)),   # K = 81 -> Kp = 96
+                                           (33, 1, 97, None), (33, 1, 97, dict(variant=1)),                # K = 33 -> Kp = 64
+                                           (7, 1, 40, dict(variant=215)), (10, 2, 333, None),              # K = 7, K = 100
+                                           (10, 2, 333, dict(ctas=148, variant=614, jsplit=2))])
+def test_partially_filled_level_blocks(gpu_lib, oracle, levels, M, B, tune):
+    """Level counts that are not multiples of 32 / 64: padded lanes, a half-filled last work unit in phase C, odd
+    successor ranges in phase B -- all bits must still match."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.synthetic(n=45, B=B, seed=levels * 100 + M, levels=levels, M=M, tie_heavy=True)
+    check_against_oracle(gpu_lib, oracle, inst.nu, inst.iterator, inst.n, inst.B, inst.df, inst.u_old, inst.beta,
+                         inst.p, inst.dt, 4, tune=tune)
+
+
 def test_large_budget_use_spans_many_slices(gpu_lib, oracle):
     """u_old far from most levels: pushes cross several CTA slices (halo depth D > 1)."""
     nu = [[0, 5, 10, 15]] * 2
