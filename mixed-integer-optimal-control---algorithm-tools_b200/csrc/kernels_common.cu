@@ -306,22 +306,26 @@ __global__ void select_kernel(Tables t, SlotDev slot, int Bnew_arg, const int *b
 // ------------------------------------------------------------------------------------------------
 // Backtrack (HelpFunctions.jl:108-122): a dependent chase of n-1 argmin entries.  With the source-row
 // indexed table one step is  b' = b - b~_l(i);  l <- arg[i-1][b'][l];  b <- b'.
-// The budget only shrinks along the trajectory and by at most max b~ per stage, so the entries the chase
-// can touch in the next S stages lie in a window of W budget rows below the current b.  The CTA brings that
-// window (S x W x Kp entries, one contiguous block per stage) and the stages' budget uses into shared memory by
-// 1-D bulk TMA, one thread chases through shared memory (two dependent LDS per stage instead of
-// two dependent HBM reads), then all threads write the S controls.  If the budget leaves the window the
-// chunk ends early and the window is re-centred.
+// The budget only shrinks along the trajectory, so the entries the chase can touch in the next S stages lie
+// in a window of W budget rows below the current b.  The CTA brings that window (S x W x Kp entries, one
+// contiguous block per stage) and the stages' budget uses into shared memory by 1-D bulk TMA, one thread
+// chases through shared memory (two dependent LDS per stage instead of two dependent HBM reads), then all
+// threads write the S controls.  Two buffers: while chunk c is chased, the window of chunk c+1 is already in
+// flight, placed below the budget known at the START of chunk c (the budget moves little within a chunk).  A
+// prefetch that turns out misplaced (the chunk ended early, or the budget fell too far) is dropped and the
+// window is reloaded around the actual budget.
 // ------------------------------------------------------------------------------------------------
 template <typename ArgT>
 __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev slot, int *err, int S, int W)
 {
     constexpr ArgT MARK = (ArgT)~(ArgT)0;
     extern __shared__ __align__(128) unsigned char smem_bt[];
-    ArgT *win = reinterpret_cast<ArgT *>(smem_bt);                                   // [S][W][Kp]
-    int *bts = reinterpret_cast<int *>(smem_bt + (size_t)S * W * t.Kp * sizeof(ArgT));  // [S][Kp]
-    int *lseq = bts + (size_t)S * t.Kp;                                              // [S]
-    __shared__ __align__(8) uint64_t s_bar;
+    const int Kp = t.Kp;
+    const uint32_t win_bytes = (uint32_t)(((size_t)S * W * Kp * sizeof(ArgT) + 127) / 128 * 128);
+    const uint32_t buf_bytes = win_bytes + (uint32_t)((size_t)S * Kp * sizeof(int));
+    // buffer k: window ArgT[S][W][Kp] at k * buf_bytes, budget uses int[S][Kp] behind it
+    int *lseq = reinterpret_cast<int *>(smem_bt + 2 * (size_t)buf_bytes);  // [S]
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_b, s_l, s_done, s_fail;
     if (slot.rec[3] != 0.) return;
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -330,40 +334,83 @@ __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev sl
         s_b = (int)slot.rec[1];
         s_l = (int)slot.rec[2];
         s_fail = 0;
-        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     for (int m = tid; m < t.M; m += NT) slot.u[m] = t.lvd[s_l * t.M + m];  // u[:,1] (:108-112)
-    uint32_t phase = 0;
-    for (long long i0 = 1; i0 <= t.n - 1;) {
-        const int cnt = (int)min((long long)S, t.n - i0);  // stages i0 .. i0+cnt-1
-        const int b0 = s_b;
-        int wb = b0 - W + 1;
+
+    // bulk-TMA the window of stages i0 .. i0+cnt-1 below budget row `top` and their budget uses into buffer k;
+    // returns the window's first budget row
+    auto issue = [&](int k, long long i0, int top) {
+        const int cnt = (int)min((long long)S, (long long)t.n - i0);
+        int wb = top - W + 1;
         if (wb < 0) wb = 0;
         const int wrows = min(W, t.B1 - wb);
-        // ---- bulk-TMA the window (one contiguous block per stage) and the stages' budget uses into shared memory
         if (tid < 32) {
-            const uint32_t wbytes = (uint32_t)((size_t)wrows * t.Kp * sizeof(ArgT));
-            if (tid == 0) mbar_expect_tx(&s_bar, (uint32_t)cnt * wbytes + (uint32_t)((size_t)cnt * t.Kp * sizeof(int)));
+            unsigned char *base = smem_bt + (size_t)k * buf_bytes;
+            const uint32_t wbytes = (uint32_t)((size_t)wrows * Kp * sizeof(ArgT));
+            if (tid == 0)
+                mbar_expect_tx(&s_bar[k], (uint32_t)cnt * wbytes + (uint32_t)((size_t)cnt * Kp * sizeof(int)));
             __syncwarp();
             for (int st = tid; st < cnt; st += 32)
-                tma_load_1d(win + (size_t)st * W * t.Kp, arg + ((size_t)(i0 + st - 1) * t.B1 + wb) * t.Kp, wbytes, &s_bar);
+                tma_load_1d(base + (size_t)st * W * Kp * sizeof(ArgT), arg + ((size_t)(i0 + st - 1) * t.B1 + wb) * Kp, wbytes,
+                            &s_bar[k]);
             if (tid == 0)
-                tma_load_1d(bts, slot.bt_all + (size_t)(i0 - 1) * t.Kp, (uint32_t)((size_t)cnt * t.Kp * sizeof(int)), &s_bar);
+                tma_load_1d(base + win_bytes, slot.bt_all + (size_t)(i0 - 1) * Kp, (uint32_t)((size_t)cnt * Kp * sizeof(int)),
+                            &s_bar[k]);
         }
-        mbar_wait(&s_bar, phase);
-        phase ^= 1u;
+        return wb;
+    };
+
+    // what the current / the other buffer holds or has in flight (identical in every thread; scalars, not arrays,
+    // so that nothing lives in local memory)
+    int cur = 0;
+    long long c_i0 = 0, o_i0 = 0;
+    int c_wb = 0, o_wb = 0;
+    bool c_live = false, o_live = false;
+    uint32_t c_phase = 0, o_phase = 0;
+    for (long long i0 = 1; i0 <= t.n - 1;) {
+        const int cnt = (int)min((long long)S, (long long)t.n - i0);  // stages i0 .. i0+cnt-1
+        const int b0 = s_b;
+        // is the block in flight for this buffer the one we need, with room for the budget to move?
+        const bool usable = c_live && c_i0 == i0 && b0 - c_wb >= min(W / 2, b0);
+        if (!usable) {
+            if (c_live) {  // let the misplaced block land before its buffer is overwritten
+                mbar_wait(&s_bar[cur], c_phase);
+                c_phase ^= 1u;
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+            c_wb = issue(cur, i0, b0);
+            c_i0 = i0;
+        }
+        mbar_wait(&s_bar[cur], c_phase);
+        c_phase ^= 1u;
+        c_live = false;
+        // the next chunk's window goes out now (the other buffer was consumed in the previous iteration)
+        if (i0 + cnt <= t.n - 1) {
+            if (o_live) {
+                mbar_wait(&s_bar[cur ^ 1], o_phase);
+                o_phase ^= 1u;
+            }
+            o_wb = issue(cur ^ 1, i0 + cnt, b0);
+            o_i0 = i0 + cnt;
+            o_live = true;
+        }
         // ---- chase through shared memory -----------------------------------------------------------------
         if (tid == 0) {
+            const ArgT *wn = reinterpret_cast<const ArgT *>(smem_bt + (size_t)cur * buf_bytes);
+            const int *bt = reinterpret_cast<const int *>(smem_bt + (size_t)cur * buf_bytes + win_bytes);
+            const int wb = c_wb, WK = W * Kp;
             int b = b0, l = s_l, st = 0, fail = 0;
-            for (; st < cnt; ++st) {
-                const int bsrc = b - bts[st * t.Kp + l];
+            for (; st < cnt; ++st, wn += WK, bt += Kp) {
+                const int bsrc = b - bt[l];
                 if (bsrc < 0) { fail = 1; break; }     // unreachable level: the reference would read stale U
                 if (bsrc < wb && st > 0) break;        // left the window: re-centre
                 // (a first step that jumps below the window reads its one entry straight from HBM)
-                const ArgT a = (bsrc >= wb) ? win[((size_t)st * W + (bsrc - wb)) * t.Kp + l]
-                                            : arg[((size_t)(i0 + st - 1) * t.B1 + bsrc) * t.Kp + l];
+                const ArgT a = (bsrc >= wb) ? wn[(bsrc - wb) * Kp + l]
+                                            : arg[((size_t)(i0 + st - 1) * t.B1 + bsrc) * Kp + l];
                 if (a == MARK || (int)a >= t.K) { fail = 1; break; }
                 l = (int)a;
                 b = bsrc;
@@ -380,11 +427,20 @@ __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev sl
         }
         if (s_fail) {
             if (tid == 0) { atomicOr(&err[1], 1); slot.rec[3] = 1.; }
-            return;
+            break;
         }
         i0 += done;  // done >= 1: the first step of a chunk always completes
-        __syncthreads();  // everyone is finished with the window before the next TMA overwrites it
+        // swap the roles of the two buffers
+        cur ^= 1;
+        { const long long x = c_i0; c_i0 = o_i0; o_i0 = x; }
+        { const int x = c_wb; c_wb = o_wb; o_wb = x; }
+        { const bool x = c_live; c_live = o_live; o_live = x; }
+        { const uint32_t x = c_phase; c_phase = o_phase; o_phase = x; }
+        __syncthreads();  // everyone is finished with the window and lseq before they are overwritten
     }
+    // never leave with a bulk copy in flight into this CTA's shared memory
+    if (c_live) mbar_wait(&s_bar[cur], c_phase);
+    if (o_live) mbar_wait(&s_bar[cur ^ 1], o_phase);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,15 +551,16 @@ void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bn
 
 void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st)
 {
-    // window rows W: at most 24 (a step that uses more budget than that falls back to one HBM read); stages per
-    // chunk S: whatever fits into ~200 KB of shared memory, at most 64
-    int W = t.B1 < 24 ? t.B1 : 24;
-    const size_t per_stage = (size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int);
-    long long S = (long long)(200 * 1024) / (long long)per_stage;
-    if (S > 64) S = 64;
-    if (S < 1) { S = 1; }
-    while (W > 1 && (size_t)S * ((size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int)) > 220 * 1024) --W;
-    const size_t smem = (size_t)S * ((size_t)W * t.Kp * argw + (size_t)t.Kp * sizeof(int) + sizeof(int)) + 128;
+    // window rows W: at most 16 (a step that uses more budget than the window holds falls back to one HBM read);
+    // stages per chunk S: at most 32, two buffers within ~200 KB of shared memory
+    int W = t.B1 < 16 ? t.B1 : 16;
+    auto per_stage = [&](int w) { return (size_t)w * t.Kp * argw + (size_t)t.Kp * sizeof(int); };
+    long long S = (long long)(100 * 1024) / (long long)per_stage(W);
+    if (S > 32) S = 32;
+    if (S < 1) S = 1;
+    while (W > 1 && 2 * (size_t)S * per_stage(W) > 200 * 1024) --W;
+    const size_t win_bytes = ((size_t)S * W * t.Kp * argw + 127) / 128 * 128;
+    const size_t smem = 2 * (win_bytes + (size_t)S * t.Kp * sizeof(int)) + (size_t)S * sizeof(int) + 128;
     if (argw == 1) {
         cudaFuncSetAttribute(backtrack_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         backtrack_kernel<uint8_t><<<1, 1024, smem, st>>>(t, slot, err, (int)S, W);
