@@ -948,22 +948,23 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     const double per_j = 7.0 * tb * c.TL + 2.0 * c.TL + ((tb + 1) / 2) + ((c.TL + 1) / 2) + 3.0;
                     return per_j * c.jper * sched * stall + 150.0;
                 };
-                // phase C is latency bound: time per unit (32 cells) and finisher warp; warps that share the SM with the
-                // scan only get the issue slots it leaves
+                // phase C is latency bound: time per unit (64 cells) and finisher warp; warps that share the SM with the
+                // scan only get the issue slots it leaves (constants fitted to tools/tune_sweep.py runs of the
+                // config-4 and the heat-shaped instance, profiles/tune_sweep*_r01.txt)
                 auto finish = [&](int rows, bool hidden) {
                     const int units = rows * ((t.Kp + 63) / 64);
                     const int per_warp = (units + c.NF - 1) / c.NF;
                     const double generic = (js == 2 || js == 4) ? 1.0 : 1.5;  // other splits: rolled combine loop
-                    return per_warp * generic * (hidden ? 400.0 + 150.0 * js : 200.0 + 80.0 * js) + 300.0;
+                    return per_warp * generic * (hidden ? 1200.0 + 50.0 * js : 100.0 + 310.0 * js) + 300.0;
                 };
                 const double sa = scan(c.TB), sb = scan(c.TBB);
                 double stage;
                 if (c.TBB > 0) {
                     const double fa = finish(c.RA, true), fb = finish(c.RB, true);
                     // a shorter finish also shortens the lag a successor slice needs behind this one
-                    stage = sa + sb + (fa > sb ? fa - sb : 0.) + (fb > sa ? fb - sa : 0.) + 0.15 * (fa + fb);
+                    stage = sa + sb + (fa > sb ? fa - sb : 0.) + (fb > sa ? fb - sa : 0.) + 0.15 * (fa + fb) + 800.0;
                 } else {
-                    stage = sa + finish(c.RA, false) + (ns == 0 ? 800.0 : 300.0);  // + the hand-over after the scan
+                    stage = sa + finish(c.RA, false) + 600.0;  // + the hand-over after the scan
                 }
                 stage += 10.0 * c.NS;  // scatter warps take issue slots from the scan
                 if (!found || stage < best_stage) {
