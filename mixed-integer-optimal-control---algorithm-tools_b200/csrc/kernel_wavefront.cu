@@ -184,14 +184,12 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
 // warp-broadcast load serves both (jb is even by construction).
 // Cost per candidate and cell on sm_100a: DADD + DSETP (two issue slots each) + 2 FSEL + SEL = 7 slots.
 template <int TB, int TL, typename ArgT>
-__device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const double *__restrict__ crow,
-                                        const double *__restrict__ srow, double *__restrict__ pv,
-                                        ArgT *__restrict__ pa, int jb, int je, int Kp)
+__device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const double *__restrict__ crow,
+                                          const double *__restrict__ srow, int jb, int je, int Kp,
+                                          double (&best)[TB][TL], int (&arg)[TB][TL])
 {
     constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
     const double inf = d_inf();
-    double best[TB][TL];
-    int arg[TB][TL];
 #pragma unroll
     for (int a = 0; a < TB; ++a)
 #pragma unroll
@@ -257,6 +255,17 @@ __device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const d
             }
         }
     }
+}
+
+// scan + partial (min, argmin) of this thread's j-group into shared memory for phase C
+template <int TB, int TL, typename ArgT>
+__device__ __forceinline__ void phase_b(const double *__restrict__ Prow, const double *__restrict__ crow,
+                                        const double *__restrict__ srow, double *__restrict__ pv,
+                                        ArgT *__restrict__ pa, int jb, int je, int Kp)
+{
+    double best[TB][TL];
+    int arg[TB][TL];
+    scan_tile<TB, TL, ArgT>(Prow, crow, srow, jb, je, Kp, best, arg);
 #pragma unroll
     for (int r = 0; r < TB; ++r)
 #pragma unroll
@@ -400,6 +409,37 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
     }
 }
 
+// With a single j-group a thread's tile already holds the final (min, argmin) of its cells: it stores the argmin
+// and scatters the values straight from registers -- no partials in shared memory, no second hand-over.
+template <int TB, int TL, typename ArgT>
+__device__ __forceinline__ void scatter_tile(const FinishArgs &a, int row0, int l0, const double (&best)[TB][TL],
+                                             const int (&arg)[TB][TL])
+{
+    const double inf = d_inf();
+    ArgT *argrow = reinterpret_cast<ArgT *>(a.argrow);
+    const int RK = a.R * a.Kp;
+    const int rows_left = a.B1 - a.r0;
+#pragma unroll
+    for (int q = 0; q < TL; ++q) {
+        const int l = l0 + q;
+        const int bt = a.bt[min(l, a.Kp - 1)];
+#pragma unroll
+        for (int r = 0; r < TB; ++r) {
+            const int row = row0 + r;
+            const bool in_tab = l < a.K && row < rows_left;
+            const int x = row * a.Kp + l;
+            const int y = x + bt * a.Kp;
+            if (in_tab && a.r0 + row < bt) a.Pn[x] = inf;  // no source row: +Inf (:47)
+            if (in_tab && row + bt < rows_left) {           // inside `for b = 0:B-b~` (:69)
+                argrow[x] = (ArgT)arg[r][q];
+                if (y < RK) a.Pn[y] = best[r][q];
+                else a.hring[y] = best[r][q];
+                if (a.phi) a.phi[y] = best[r][q];
+            }
+        }
+    }
+}
+
 // Phase C and the terminal stage for the rows of one CTA, executed by NF "finisher" warps: the scatter warps, or --
 // for tiles without a second sub-slice -- the compute warps themselves after their scan.
 template <typename ArgT>
@@ -459,6 +499,22 @@ struct Finisher {
                 if ((++spins & 0xfffffu) == 0 && *(volatile int *)&c.err[3]) break;  // the comm warp gave up
             }
         }
+    }
+
+    __device__ __forceinline__ FinishArgs stage_args(const SlotDev &sl, int i, long long T) const
+    {
+        const int Kp = t.Kp, B1 = t.B1, R = c.R;
+        FinishArgs a;
+        a.pv = sm.pv;
+        a.pa = sm.pa;
+        a.bt = sm.bts + (size_t)(T % 3) * Kp;
+        a.umap = sm.umap;
+        a.Pn = sm.Ps + (size_t)((i - 1) & 1) * R * Kp;
+        a.hring = c.halo + ((size_t)(T % kHaloRing) * B1 + r0) * Kp;
+        a.phi = (i <= 2) ? sl.phi + ((size_t)((i + 1) & 1) * B1 + r0) * Kp : nullptr;
+        a.argrow = reinterpret_cast<unsigned char *>(sl.arg) + ((size_t)(i - 1) * B1 + r0) * Kp * sizeof(ArgT);
+        a.JS = c.JS; a.R = R; a.Kp = Kp; a.K = t.K; a.B1 = B1; a.r0 = r0;
+        return a;
     }
 
     // phase C of work units [ub, ue) of stage i (global step T)
@@ -790,6 +846,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 
     // tiles without a second sub-slice have no scatter warps: the compute warps finish their own stage
     const bool self_finish = (TBB == 0) && (c.NS == 0);  // two sub-slices always have scatter warps
+    const bool direct = self_finish && c.JS == 1;         // final values stay in registers until they are scattered
     const int cwarp = tid >> 5;
     Finisher<ArgT> fin(t, c, sm, cwarp, NC >> 5, lane);
     uint32_t scanned_phase = 0;
@@ -817,6 +874,21 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             // ---- phase B: register-tiled min-plus scan over this group's successors, sub-slice A then B ------
             wait_finished(0);  // rows of A for stage i are complete (finish(A, i+1) or the terminal stage)
             PROF_LAP(0);
+            if (direct) {
+                // ---- one j-group, no scatter warps: scan, then scatter the finished tile from registers ------------
+                double best[TBA][TL];
+                int arg[TBA][TL];
+                if (active) scan_tile<TBA, TL, ArgT>(Pc + (size_t)rowA * Kp, sm.cs + lg * TL, ssc + lg * TL, 0, K, Kp, best, arg);
+                PROF_LAP(1);
+                scanned(0);  // the comm warp may refill the rows this stage read
+                fin.wait_inputs(i, T);
+                PROF_LAP(2);
+                if (active) scatter_tile<TBA, TL, ArgT>(fin.stage_args(sl, i, T), rowA, lg * TL, best, arg);
+                finished();
+                PROF_LAP(3);
+                pc[4] += 1;
+                continue;
+            }
             if (active)
                 phase_b<TBA, TL, ArgT>(Pc + (size_t)rowA * Kp, sm.cs + lg * TL, ssc + lg * TL,
                                        sm.pv + ((size_t)jg * R + rowA) * Kp + lg * TL,
@@ -964,7 +1036,10 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     // a shorter finish also shortens the lag a successor slice needs behind this one
                     stage = sa + sb + (fa > sb ? fa - sb : 0.) + (fb > sa ? fb - sa : 0.) + 0.15 * (fa + fb) + 800.0;
                 } else {
-                    stage = sa + finish(c.RA, false) + 600.0;  // + the hand-over after the scan
+                    if (js == 1 && ns == 0)  // direct: the finished tile is scattered from registers, one hand-over
+                        stage = sa + 14.0 * c.TB * c.TL * sched + 450.0;
+                    else
+                        stage = sa + finish(c.RA, false) + 600.0;  // + the hand-over after the scan
                 }
                 stage += 10.0 * c.NS;  // scatter warps take issue slots from the scan
                 if (!found || stage < best_stage) {
