@@ -197,18 +197,25 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false)
         p->launches += 1;
         p->last_path = 2;
     } else if (p->wave_ok) {
-        CU(cudaMemsetAsync(p->d_flags, 0, (size_t)p->cfg.G * kFlagStride * sizeof(unsigned long long), st));
-        WaveCfg c = p->cfg;
-        c.nsub = count;
-        c.slots = p->d_slots + slot0;
-        c.halo = p->d_halo;
-        c.flags = p->d_flags;
-        c.err = p->d_err;
-        c.btmax = p->d_btmax;
-        c.prof = p->prof_on ? p->d_prof : nullptr;
-        c.decouple = (p->prof_on && getenv("BELLMAN_B200_DECOUPLE")) ? 1 : 0;  // profiling experiment, never a result
+        // the kernel counts global steps (slots * n) in 32 bits: very long batches go out in several launches
+        const long long per_launch = ((((long long)1 << 30) - 1) / p->n) > 0 ? ((((long long)1 << 30) - 1) / p->n) : 1;
         if (!capturing) CU(cudaEventRecord(p->ev[4], st));
-        CU(launch_wavefront(p->tab, c, p->argw, st));
+        for (int done = 0; done < count;) {
+            const int chunk = (int)((long long)(count - done) < per_launch ? (count - done) : per_launch);
+            CU(cudaMemsetAsync(p->d_flags, 0, (size_t)p->cfg.G * kFlagStride * sizeof(unsigned long long), st));
+            WaveCfg c = p->cfg;
+            c.nsub = chunk;
+            c.slots = p->d_slots + slot0 + done;
+            c.halo = p->d_halo;
+            c.flags = p->d_flags;
+            c.err = p->d_err;
+            c.btmax = p->d_btmax;
+            c.prof = p->prof_on ? p->d_prof : nullptr;
+            c.decouple = (p->prof_on && getenv("BELLMAN_B200_DECOUPLE")) ? atoi(getenv("BELLMAN_B200_DECOUPLE")) : 0;  // profiling experiment, never a result
+            CU(launch_wavefront(p->tab, c, p->argw, st));
+            done += chunk;
+            if (done < count) p->launches += 1;
+        }
         if (!capturing) CU(cudaEventRecord(p->ev[5], st));
         p->launches += 1;
         p->last_path = 1;

@@ -100,6 +100,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait parks the warp in hardware until the phase completes or the time hint expires; without a hint it returns
+// almost at once and a waiting warp burns the issue slots of the warps that share its scheduler (the waiting loops
+// executed half as many instructions as the scan before the hint was added).
+constexpr uint32_t kMbarSuspendNs = 1000000u;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t done = 0;
@@ -107,11 +111,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
             : "memory");
     }
 }

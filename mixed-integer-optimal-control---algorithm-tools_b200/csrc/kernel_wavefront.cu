@@ -57,6 +57,10 @@ __device__ __forceinline__ unsigned long long lds_acquire(const uint64_t *p)
     asm volatile("ld.acquire.cta.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts_release_u32(uint64_t *p, unsigned int v)
+{
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts_release(uint64_t *p, unsigned long long v)
 {
     asm volatile("st.release.cta.shared::cta.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
@@ -73,13 +77,13 @@ __device__ __forceinline__ unsigned int lds_acquire_u32(const uint64_t *p)
     return v;
 }
 // has the counter reached `want` events?  (events are counted modulo 2^32; the lag is always far below 2^31)
-__device__ __forceinline__ bool reached(unsigned int cnt, unsigned long long want) { return (int)(cnt - (unsigned int)want) >= 0; }
+__device__ __forceinline__ bool reached(unsigned int cnt, unsigned int want) { return (int)(cnt - want) >= 0; }
 
 // mbarrier wait with a watchdog: a lost hand-over becomes an error code (err[2] watchdog, err[3] abort) instead of
-// a hung GPU.  Once the abort flag is up every wait gives up quickly so that the launch drains.
-__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int *err)
+// a hung GPU.  Once the abort flag is up every wait gives up quickly so that the launch drains.  The waiting loop is
+// ONE out-of-line copy: the kernel's hot code has to stay below the 32 KB instruction-cache tier.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int *err)
 {
-    if (mbar_test(bar, parity)) return;
     unsigned int spins = 0;
     long long t0 = 0;
     for (;;) {
@@ -87,18 +91,18 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(bar_addr), "r"(parity), "r"(kMbarSuspendNs)
             : "memory");
         if (done) return;
-        if ((++spins & 0x3ffu) == 0) {
+        if ((++spins & 0x3fu) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             if (*(volatile int *)&err[3]) {
-                if (spins >= 4096u) return;
+                if (spins >= 256u) return;
             } else if (now - t0 > 6000000000LL) {  // ~3 s
                 atomicOr(&err[2], 2);
                 atomicOr(&err[3], 1);
@@ -106,6 +110,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
             }
         }
     }
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int *err)
+{
+    if (mbar_test(bar, parity)) return;
+    mbar_wait_slow(smem_u32(bar), parity, err);
 }
 
 #ifndef BB_COMM_SLEEP
@@ -118,10 +127,10 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
 #define BB_UNROLL 4
 #endif
 #ifndef BB_CU
-#define BB_CU 2
+#define BB_CU 1
 #endif
 constexpr int kUnrollB = BB_UNROLL;  // successor pairs per trip of the phase-B loop
-constexpr long long kNever = (long long)1 << 62;
+constexpr int kNever = 0x7fffffff;  // "no bound": ticks are 32-bit, wave_configure refuses launches with >= 2^30 steps
 
 // shared-memory synchronisation words
 enum {
@@ -156,7 +165,7 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
                              3 * (size_t)t.Kp * sizeof(double),
                              3 * (size_t)t.Kp * sizeof(int),
                              2 * (size_t)t.Kp * c.R * sizeof(double),
-                             (size_t)t.K * t.Kp * sizeof(double),
+                             (size_t)c.Kr * t.Kp * sizeof(double),
                              (size_t)c.JS * c.R * t.Kp * sizeof(double),
                              (size_t)c.JS * c.R * t.Kp * (size_t)argw,
                              (size_t)c.R * (t.Kp / 32) * sizeof(int)};
@@ -198,7 +207,11 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 #pragma unroll
     for (int q = 0; q < TL; ++q) s[q] = srow[q];
     // main loop: full pairs, one straight-line block so that the two candidates' chains interleave
+#ifdef BB_EXP_SMALL
+    const int je2 = jb + 32;  // EXPERIMENT ONLY: config 4 with four j-groups (pad columns/rows hold +Inf)
+#else
     const int je2 = jb + ((je - jb) & ~1);
+#endif
 #pragma unroll kUnrollB
     for (int j = jb; j < je2; j += 2) {
         double p0[TB], p1[TB];
@@ -243,6 +256,7 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
             }
         }
     }
+#ifndef BB_EXP_SMALL
     if (je2 < je) {  // odd tail: one last successor
         const int j = je2;
 #pragma unroll
@@ -255,6 +269,7 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
             }
         }
     }
+#endif
 }
 
 // scan + partial (min, argmin) of this thread's j-group into shared memory for phase C
@@ -292,12 +307,13 @@ struct FinishArgs {
 // overlap.  A unit is 64 consecutive levels of one source row; a lane owns two neighbouring cells and fetches
 // their partial minima with one 16-byte load per j-group (and both argmins with one 2-byte load).  Units [ub, ue)
 // of the CTA belong to the sub-slice being finished; warp sw of NS takes every NS-th one.
-template <int JSC, typename ArgT>
+template <int JSC, typename ArgT, bool PROF>
 __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue, int sw, int NS, int lane, long long *pcc)
 {
     static_assert(sizeof(ArgT) == 1, "the packed two-cell argmin load assumes one byte per cell");
-    long long tq0 = pcc ? clock64() : 0;
-    constexpr int CU = BB_CU;
+    long long tq0 = 0;
+    if constexpr (PROF) tq0 = pcc ? clock64() : 0;
+    constexpr int CU = BB_CU;  // units in flight per warp: 1 keeps the code small (instruction cache), see DESIGN.md
     const double inf = d_inf();
     const double *__restrict__ pv = a.pv;
     const unsigned char *__restrict__ pa = a.pa;
@@ -388,7 +404,7 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
 #pragma unroll
             for (int u = 0; u < CU; ++u) { arg[u][0] = gw[u][0] & 0xff; arg[u][1] = gw[u][1] >> 8; }
         }
-        if (pcc) { const long long tq = clock64(); pcc[0] += tq - tq0; tq0 = tq; }
+        if constexpr (PROF) { if (pcc) { const long long tq = clock64(); pcc[0] += tq - tq0; tq0 = tq; } }
 #pragma unroll
         for (int u = 0; u < CU; ++u)
 #pragma unroll
@@ -405,7 +421,7 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
                 for (int e = 0; e < 2; ++e)
                     if (ok[u][e]) a.phi[y_[u][e]] = val[u][e];
         }
-        if (pcc) { const long long tq = clock64(); pcc[1] += tq - tq0; tq0 = tq; }
+        if constexpr (PROF) { if (pcc) { const long long tq = clock64(); pcc[1] += tq - tq0; tq0 = tq; } }
     }
 }
 
@@ -442,7 +458,7 @@ __device__ __forceinline__ void scatter_tile(const FinishArgs &a, int row0, int 
 
 // Phase C and the terminal stage for the rows of one CTA, executed by NF "finisher" warps: the scatter warps, or --
 // for tiles without a second sub-slice -- the compute warps themselves after their scan.
-template <typename ArgT>
+template <typename ArgT, bool PROF>
 struct Finisher {
     const Tables &t;
     const WaveCfg &c;
@@ -463,7 +479,7 @@ struct Finisher {
     }
 
     // terminal stage n (HelpFunctions.jl:27-43) = the rows stage n-1 reads:  P[b][l] = (b == b~_l(n)) ? s_l(n) : Inf
-    __device__ __forceinline__ void terminal(const SlotDev &sl, long long T)
+    __device__ __forceinline__ void terminal(const SlotDev &sl, int T)
     {
         const int K = t.K, Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n;
         const double inf = d_inf();
@@ -483,7 +499,7 @@ struct Finisher {
     }
 
     // before the first store of stage i: halo rows landed, ring slot free
-    __device__ __forceinline__ void wait_inputs(int i, long long T)
+    __device__ __forceinline__ void wait_inputs(int i, int T)
     {
         // my next rows receive the lower slices' block by TMA (issued by the comm warp): it must have landed before
         // my own results overwrite the cells I produce myself
@@ -494,14 +510,14 @@ struct Finisher {
         // back-pressure: the successors consumed the ring slot this step overwrites
         if (pushes) {
             unsigned int spins = 0;
-            while ((long long)lds_acquire(&sm.mbar[RING_OK]) < T) {
+            while ((int)lds_acquire_u32(&sm.mbar[RING_OK]) < T) {
                 __nanosleep(64);
                 if ((++spins & 0xfffffu) == 0 && *(volatile int *)&c.err[3]) break;  // the comm warp gave up
             }
         }
     }
 
-    __device__ __forceinline__ FinishArgs stage_args(const SlotDev &sl, int i, long long T) const
+    __device__ __forceinline__ FinishArgs stage_args(const SlotDev &sl, int i, int T) const
     {
         const int Kp = t.Kp, B1 = t.B1, R = c.R;
         FinishArgs a;
@@ -518,7 +534,7 @@ struct Finisher {
     }
 
     // phase C of work units [ub, ue) of stage i (global step T)
-    __device__ __forceinline__ void rows(const SlotDev &sl, int i, long long T, int ub, int ue)
+    __device__ __forceinline__ void rows(const SlotDev &sl, int i, int T, int ub, int ue)
     {
         const int Kp = t.Kp, B1 = t.B1, R = c.R;
         FinishArgs a;
@@ -531,28 +547,32 @@ struct Finisher {
         a.phi = (i <= 2) ? sl.phi + ((size_t)((i + 1) & 1) * B1 + r0) * Kp : nullptr;
         a.argrow = reinterpret_cast<unsigned char *>(sl.arg) + ((size_t)(i - 1) * B1 + r0) * Kp * sizeof(ArgT);
         a.JS = c.JS; a.R = R; a.Kp = Kp; a.K = t.K; a.B1 = B1; a.r0 = r0;
-        long long *pccp = c.prof ? pcc : nullptr;
+        long long *pccp = (PROF && c.prof) ? pcc : nullptr;
+#ifdef BB_EXP_SMALL
+        finish_rows<4, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp);
+#else
         switch (c.JS) {
-            case 2: finish_rows<2, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
-            case 4: finish_rows<4, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
-            default: finish_rows<0, ArgT>(a, ub, ue, fw, NF, lane, pccp); break;
+            case 2: finish_rows<2, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
+            case 4: finish_rows<4, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
+            default: finish_rows<0, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
         }
+#endif
     }
 };
 
-template <typename ArgT>
+template <typename ArgT, bool PROF>
 __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int sw, int lane)
 {
     const int g = blockIdx.x;
     const int R = c.R, n = t.n;
     const int NV = c.RB > 0 ? 2 : 1;
-    Finisher<ArgT> fin(t, c, sm, sw, c.NS, lane);
+    Finisher<ArgT, PROF> fin(t, c, sm, sw, c.NS, lane);
     const int ublocks = fin.ublocks;
     uint32_t cost_phase = 0, scanned_phase = 0;
     long long pc[3] = {0, 0, 0};  // profile (warp 0): wait for the scan, wait for halo / ring, work
     long long tp = clock64();
-#define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
-    auto wait_costs = [&](long long T) {
+#define PROF_LAP(k) do { if constexpr (PROF) { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } } while (0)
+    auto wait_costs = [&](int T) {
         const int b = (int)(T % 3);
         mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err);
         cost_phase ^= 1u << b;
@@ -565,7 +585,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
         }
     };
 
-    long long T = 0;  // global step: subproblem * n + (n - stage)
+    int T = 0;  // global step: subproblem * n + (n - stage)
     for (int sub = 0; sub < c.nsub; ++sub) {
         const SlotDev sl = c.slots[sub];
         wait_costs(T);
@@ -583,13 +603,13 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
                     PROF_LAP(1);
                 }
                 const int ub = v == 0 ? 0 : c.RA * ublocks, ue = v == 0 ? c.RA * ublocks : R * ublocks;
-                fin.rows(sl, i, T, ub, ue);
+                if (c.decouple < 2) fin.rows(sl, i, T, ub, ue);
                 finished(v);
                 PROF_LAP(2);
             }
         }
     }
-    if (c.prof && sw == 0 && lane == 0) {
+    if (PROF && c.prof && sw == 0 && lane == 0) {
         for (int k = 0; k < 3; ++k) c.prof[(size_t)g * 16 + 5 + k] = pc[k];
         c.prof[(size_t)g * 16 + 14] = fin.pcc[0];
         c.prof[(size_t)g * 16 + 15] = fin.pcc[1];
@@ -606,15 +626,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
 //          that buffer (they finished scanning stage i+1);
 //   ring:  how far this CTA's pushes may run ahead of the slowest successor (ring of kHaloRing slots).
 // A bounded watchdog turns a lost dependency into an error code instead of a hung GPU.
-__device__ __forceinline__ long long warp_min(long long v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = w < v ? w : v;
-    }
-    return v;
-}
+__device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 
 __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane)
 {
@@ -626,24 +638,24 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
     const int D = (btm + R - 1) / R;  // slices a push can span
     const int my_rows = min(R, B1 - r0);  // rows of this slice that exist in the table (>= 1)
     const int npred = min(D, g), nsucc = min(D, c.G - 1 - g);
-    const long long Ttot = (long long)c.nsub * n;
+    const int Ttot = c.nsub * n;
     // cost cursor
-    long long cT = 0;
+    int cT = 0;
     int csub = 0, ck = 0;
     // halo cursor: stage i = n - hk, hk in [1, n-2]
     bool h_active = (npred > 0 && n >= 3);
     int hsub = 0, hk = 1;
-    long long pred_seen = 0;
+    int pred_seen = 0;
     // ring cursor
-    long long ring_val = (c.G - 1 - g > 0) ? (long long)(kHaloRing - 1) : kNever;  // value set at kernel start
+    int ring_val = (c.G - 1 - g > 0) ? (kHaloRing - 1) : kNever;  // value set at kernel start
     if (nsucc == 0 && ring_val != kNever) {  // successors exist but never receive pushes (b~ = 0 everywhere)
         ring_val = kNever;
-        if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+        if (lane == 0) sts_release_u32(&sm.mbar[RING_OK], (unsigned int)ring_val);
     }
     if (c.decouple) {  // timing experiment only (results are wrong): ignore the neighbours
         pred_seen = kNever;
         ring_val = kNever;
-        if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+        if (lane == 0) sts_release_u32(&sm.mbar[RING_OK], (unsigned int)ring_val);
     }
     unsigned int idle = 0;
     long long pc[6] = {0, 0, 0, 0, 0, 0};  // profile: loop trips, idle trips, pred polls, succ polls, SM id, cost rows loaded
@@ -654,7 +666,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         const unsigned int scn_cnt = lds_acquire_u32(&sm.mbar[CNT_SCANNED]);   // ncw arrivals per scanned stage
         pc[0] += 1;
         // ---- cost cursor --------------------------------------------------------------------------------
-        while (cT < Ttot && (cT < 3 || reached(fin_cnt, (unsigned long long)(cT - 2) * NF))) {
+        while (cT < Ttot && (cT < 3 || reached(fin_cnt, (unsigned int)(cT - 2) * (unsigned int)NF))) {
             if (lane == 0) {
                 const SlotDev &sl = c.slots[csub];
                 const int b = (int)(cT % 3);
@@ -671,19 +683,19 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         }
         // ---- halo cursor --------------------------------------------------------------------------------
         if (h_active) {
-            const long long hT = (long long)hsub * n + hk;
+            const int hT = hsub * n + hk;
             if (pred_seen < hT) {
-                long long m = kNever;
+                int m = kNever;
 #pragma unroll 1
                 for (int idx = lane; idx < npred; idx += 32)
-                    m = min(m, (long long)ld_acquire(c.flags + (size_t)(g - idx - 1) * kFlagStride));
+                    m = min(m, (int)ld_acquire(c.flags + (size_t)(g - idx - 1) * kFlagStride));
                 pred_seen = max(pred_seen, warp_min(m));
                 __syncwarp();  // every polling lane finished its acquire load; lane 0 inherits the order
                 pc[2] += 1;
             }
             // the buffer the block lands in was last read by the scan of stage i+1 (or by the previous subproblem)
-            const long long need_scanned = (long long)hsub * (n - 1) + hk - 1;
-            if (pred_seen >= hT && reached(scn_cnt, (unsigned long long)need_scanned * ncw)) {
+            const int need_scanned = hsub * (n - 1) + hk - 1;
+            if (pred_seen >= hT && reached(scn_cnt, (unsigned int)need_scanned * (unsigned int)ncw)) {
                 if (lane == 0) {
                     const int i = n - hk;
                     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy read
@@ -700,17 +712,17 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         // ---- ring cursor --------------------------------------------------------------------------------
         // scatter warps work on step >= cT - 3 at most cT: keep the ring bound a few steps ahead of them
         if (ring_val < Ttot && ring_val < cT + 2) {
-            long long m = kNever;
+            int m = kNever;
 #pragma unroll 1
             for (int idx = lane; idx < nsucc; idx += 32)
-                m = min(m, (long long)ld_acquire(c.flags + (size_t)(g + idx + 1) * kFlagStride));
+                m = min(m, (int)ld_acquire(c.flags + (size_t)(g + idx + 1) * kFlagStride));
             m = warp_min(m);
             __syncwarp();
             pc[3] += 1;
-            const long long nv = (m >= kNever) ? kNever : m + kHaloRing - 1;
+            const int nv = (m >= kNever) ? kNever : m + kHaloRing - 1;
             if (nv > ring_val) {
                 ring_val = nv;
-                if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+                if (lane == 0) sts_release_u32(&sm.mbar[RING_OK], (unsigned int)ring_val);
                 progress = true;
             }
         }
@@ -728,7 +740,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
             if (abort_now) {  // give up on the neighbours so that this CTA drains and the launch ends
                 pred_seen = kNever;
                 ring_val = kNever;
-                if (lane == 0) sts_release(&sm.mbar[RING_OK], (unsigned long long)ring_val);
+                if (lane == 0) sts_release_u32(&sm.mbar[RING_OK], (unsigned int)ring_val);
             }
         }
     }
@@ -750,11 +762,11 @@ __device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c
     const int g = blockIdx.x;
     const int n = t.n;
     unsigned long long *myflag = c.flags + (size_t)g * kFlagStride;
-    long long T = 0;
+    int T = 0;
     for (int sub = 0; sub < c.nsub; ++sub) {
         ++T;  // the terminal stage pushes nothing
         for (int i = n - 1; i >= 1; --i, ++T) {
-            const unsigned long long want = (unsigned long long)(T + 1) * (unsigned)c.NF;
+            const unsigned int want = (unsigned int)(T + 1) * (unsigned int)c.NF;
             unsigned int spins = 0;
             while (!reached(lds_acquire_u32(&sm.mbar[CNT_FINISHED]), want)) {
                 __nanosleep(BB_PUB_SLEEP);  // a quiet poll: this warp shares a scheduler with compute warps
@@ -768,7 +780,7 @@ __device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c
 
 // MAXT is a multiple of 128: the register file is split evenly over the four schedulers, so the per-thread
 // budget is set by the scheduler that hosts the most warps.
-template <int TBA, int TBB, int TL, typename ArgT, int MAXT>
+template <int TBA, int TBB, int TL, typename ArgT, int MAXT, bool PROF>
 __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -783,7 +795,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     const double inf = d_inf();
 
     // one-time: jump costs into shared memory, value rows to +Inf, barriers and counters
-    for (int x = tid; x < K * Kp; x += blockDim.x) sm.cs[x] = t.cost[x];
+    for (int x = tid; x < c.Kr * Kp; x += blockDim.x) sm.cs[x] = x < K * Kp ? t.cost[x] : inf;  // pad rows: never win
     for (int x = tid; x < 2 * R * Kp; x += blockDim.x) sm.Ps[x] = inf;
     for (int x = tid; x < R * ((Kp + 63) >> 6); x += blockDim.x)
         sm.umap[x] = ((x / ((Kp + 63) >> 6)) << 16) | ((x % ((Kp + 63) >> 6)) << 6);
@@ -795,13 +807,13 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         }
         sm.mbar[CNT_SCANNED] = 0;
         sm.mbar[CNT_FINISHED] = 0;
-        sm.mbar[RING_OK] = (g + 1 < c.G) ? (uint64_t)(kHaloRing - 1) : (uint64_t)kNever;
+        sm.mbar[RING_OK] = (g + 1 < c.G) ? (uint64_t)(kHaloRing - 1) : (uint64_t)kNever;  // read as a 32-bit tick
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (tid >= NC + 64) {
-        scatter_warp<ArgT>(t, c, sm, (tid - NC - 64) >> 5, tid & 31);
+        scatter_warp<ArgT, PROF>(t, c, sm, (tid - NC - 64) >> 5, tid & 31);
         return;
     }
     if (tid >= NC + 32) {
@@ -819,13 +831,13 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     const int rg = active ? tig / c.nLG : 0;
     const int lg = active ? tig % c.nLG : 0;
     const int jb = jg * c.jper;
-    const int je = min(K, jb + c.jper);
+    const int je = min(c.Kr, jb + c.jper);  // rows K .. Kr-1 of the cost table are +Inf: (s + Inf) + P never wins
     const int lane = tid & 31;
     uint32_t cost_phase = 0, fin_phase = 0;
     long long pc[5] = {0, 0, 0, 0, 0};  // profile: wait A (+ costs), phase B, hand-over, wait B, stages
     long long tp = clock64();
-#define PROF_LAP(k) do { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } while (0)
-    auto wait_costs = [&](long long T) {
+#define PROF_LAP(k) do { if constexpr (PROF) { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } } while (0)
+    auto wait_costs = [&](int T) {
         const int b = (int)(T % 3);
         mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err);
         cost_phase ^= 1u << b;
@@ -848,7 +860,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     const bool self_finish = (TBB == 0) && (c.NS == 0);  // two sub-slices always have scatter warps
     const bool direct = self_finish && c.JS == 1;         // final values stay in registers until they are scattered
     const int cwarp = tid >> 5;
-    Finisher<ArgT> fin(t, c, sm, cwarp, NC >> 5, lane);
+    Finisher<ArgT, PROF> fin(t, c, sm, cwarp, NC >> 5, lane);
     uint32_t scanned_phase = 0;
     auto finished = [&]() {
         __syncwarp();
@@ -858,7 +870,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         }
     };
 
-    long long T = 0;
+    int T = 0;
     for (int sub = 0; sub < c.nsub; ++sub) {
         const SlotDev sl = c.slots[sub];
         wait_costs(T);  // terminal stage: nothing to scan, but every role follows every cost phase
@@ -878,7 +890,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 // ---- one j-group, no scatter warps: scan, then scatter the finished tile from registers ------------
                 double best[TBA][TL];
                 int arg[TBA][TL];
-                if (active) scan_tile<TBA, TL, ArgT>(Pc + (size_t)rowA * Kp, sm.cs + lg * TL, ssc + lg * TL, 0, K, Kp, best, arg);
+                if (active) scan_tile<TBA, TL, ArgT>(Pc + (size_t)rowA * Kp, sm.cs + lg * TL, ssc + lg * TL, 0, c.Kr, Kp, best, arg);
                 PROF_LAP(1);
                 scanned(0);  // the comm warp may refill the rows this stage read
                 fin.wait_inputs(i, T);
@@ -921,11 +933,11 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         // drain: stage 1 (or the terminal stage when n == 1) is finished; keeps the barrier phases aligned
         for (int v = 0; v < NV; ++v) wait_finished(v);
     }
-    if (c.prof && tid == 0 && self_finish) {
+    if (PROF && c.prof && tid == 0 && self_finish) {
         c.prof[(size_t)g * 16 + 14] = fin.pcc[0];
         c.prof[(size_t)g * 16 + 15] = fin.pcc[1];
     }
-    if (c.prof && tid == 0) {
+    if (PROF && c.prof && tid == 0) {
         c.prof[(size_t)g * 16 + 0] = pc[0];
         c.prof[(size_t)g * 16 + 1] = pc[1];
         c.prof[(size_t)g * 16 + 2] = pc[2];
@@ -969,6 +981,15 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int N
     c.nLG = (t.K + c.TL - 1) / c.TL;
     c.JS = JS;
     c.jper = ((t.K + JS - 1) / JS + 1) & ~1;  // even: successors are taken in aligned pairs
+    // Pad the successor axis with +Inf cost rows up to whole trips of the unrolled scan loop (8 successors) when the
+    // value rows are wide enough (Kp columns exist) -- every j-group then runs the same straight-line loop and the
+    // remainder / odd-tail code stays cold (instruction cache).  Otherwise exactly K rows.
+    {
+        const int jper8 = (c.jper + 7) & ~7;
+        const int need = JS * jper8;
+        if (need <= t.Kp) { c.jper = jper8; c.Kr = need; }
+        else c.Kr = t.K;
+    }
     c.tpg = ((c.RG * c.nLG + 31) / 32) * 32;
     c.NS = NS;
     c.NF = c.NS > 0 ? c.NS : c.JS * c.tpg / 32;  // warps that finish a stage: scatter warps, else the compute warps
@@ -980,6 +1001,7 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     int want_variant, WaveCfg &cfg)
 {
     if (t.M > kMaxM || argw != 1) return false;  // K > 255: the jump-cost table would not fit in shared memory anyway
+    if ((long long)t.n >= ((long long)1 << 30)) return false;  // ticks are 32-bit; the host splits long batches into launches
     const int want_ns = want_variant / 100;  // 0: automatic, 1..8: that many scatter warps, 10: none (NS = 0)
     want_variant %= 100;
     static const int kNsChoices[] = {0, 1, 2, 3, 4, 6, 8};
@@ -1057,7 +1079,9 @@ template <int TBA, int TBB, int TL>
 static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStream_t st)
 {
     void *args[] = {(void *)&t, (void *)&cfg};
-    const void *fn = (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, kWaveThreads>;
+    // the cycle counters are a separate instantiation: their code would cost the production kernel ~1.5 %
+    const void *fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, kWaveThreads, true>
+                              : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, kWaveThreads, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     // cooperative launch: the CTAs wait on one another, so all of them must be co-resident

@@ -25,7 +25,8 @@ struct WaveCfg {
     int RA, RB;   // rows of sub-slice A (lower) and B (upper): RG * TB, RG * TBB
     int nLG;      // level groups = ceil(K / TL)
     int JS;       // j-split: thread groups scanning disjoint successor ranges
-    int jper;     // successors per group = ceil(K / JS), rounded up to even
+    int jper;     // successors per group = ceil(K / JS), rounded up to even (to 8 when the pad rows fit)
+    int Kr;       // rows of the jump-cost table in shared memory: K, or JS * jper with +Inf pad rows
     int tpg;      // threads per group (multiple of 32)
     int NS;       // scatter warps (phase C); 0 when the tile has one sub-slice and the compute warps finish it
     int NF;       // warps that finish a stage: NS, or the compute warps

@@ -153,12 +153,31 @@ __global__ void __launch_bounds__(512, 1) probe(long long *out, int stages)
     for (int x = threadIdx.x; x < Kp; x += blockDim.x) ss[x] = x * 0.125;
     __syncthreads();
     const int tid = threadIdx.x;
-    if (tid >= 256) return;
+    __shared__ volatile int done_flag;
+    __shared__ unsigned long long bar;
+    if (tid == 0) {
+        done_flag = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar)), "r"(1));
+    }
+    __syncthreads();
+    if (tid >= 256) {
+        // MODE 4/6: helper warps that poll shared memory between short sleeps (like the comm / publisher warps);
+        // MODE 5: helper warps parked on an mbarrier (like the scatter warps waiting for the scan)
+        if (MODE == 4 || MODE == 6) {
+            while (!done_flag) __nanosleep(MODE == 4 ? 64 : 1000);
+        } else if (MODE == 5) {
+            unsigned ok = 0;
+            while (!ok && !done_flag)
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(&bar)), "r"(0) : "memory");
+        }
+        return;
+    }
     const int jg = tid / 64, lg = tid % 64;
     const int jb = jg * 32, je = jb + 32;
     const long long t0 = clock64();
     for (int sidx = 0; sidx < stages; ++sidx) {
-        if (MODE == 0) {
+        if (MODE == 0 || MODE >= 4) {
             scan_percand<4, 2>(P, cs + lg * 2, ss + lg * 2, pv + (size_t)jg * R * Kp + lg * 2, pa + (size_t)jg * R * Kp + lg * 2, jb, je, Kp);
             scan_percand<3, 2>(P + 4 * Kp, cs + lg * 2, ss + lg * 2, pv + ((size_t)jg * R + 4) * Kp + lg * 2, pa + ((size_t)jg * R + 4) * Kp + lg * 2, jb, je, Kp);
         } else if (MODE == 1) {
@@ -174,7 +193,12 @@ __global__ void __launch_bounds__(512, 1) probe(long long *out, int stages)
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const long long t1 = clock64();
-    if (tid == 0) out[blockIdx.x] = (t1 - t0) / stages;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid == 0) {
+        out[blockIdx.x] = (t1 - t0) / stages;
+        done_flag = 1;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&bar)) : "memory");
+    }
 }
 
 template <int MODE>
@@ -203,5 +227,8 @@ int main()
     run<1>("blocked (8) argmin, tiles 4x2 + 3x2");
     run<2>("per-candidate argmin, tile 7x2");
     run<3>("blocked (8) argmin, tile 7x2");
+    run<4>("per-candidate 4x2+3x2, + 8 warps polling smem / nanosleep(64)");
+    run<6>("per-candidate 4x2+3x2, + 8 warps polling smem / nanosleep(1000)");
+    run<5>("per-candidate 4x2+3x2, + 8 warps parked on an mbarrier");
     return 0;
 }
