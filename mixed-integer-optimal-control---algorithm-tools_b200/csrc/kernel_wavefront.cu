@@ -469,6 +469,7 @@ struct Finisher {
     bool halo_on, pushes;
     uint32_t halo_phase = 0;
     long long pcc[2] = {0, 0};  // profile: loads + combine, stores
+    long long ring_wait = 0;    // profile: cycles spent waiting for ring space
 
     __device__ __forceinline__ Finisher(const Tables &t_, const WaveCfg &c_, const Smem &sm_, int fw_, int NF_, int lane_)
         : t(t_), c(c_), sm(sm_), fw(fw_), NF(NF_), lane(lane_), r0(blockIdx.x * c_.R), lblocks(t_.Kp >> 5), ublocks((t_.Kp + 63) >> 6)
@@ -508,6 +509,8 @@ struct Finisher {
             halo_phase ^= 1u << (i & 1);
         }
         // back-pressure: the successors consumed the ring slot this step overwrites
+        long long tr0 = 0;
+        if constexpr (PROF) tr0 = clock64();
         if (pushes) {
             unsigned int spins = 0;
             while ((int)lds_acquire_u32(&sm.mbar[RING_OK]) < T) {
@@ -515,6 +518,7 @@ struct Finisher {
                 if ((++spins & 0xfffffu) == 0 && *(volatile int *)&c.err[3]) break;  // the comm warp gave up
             }
         }
+        if constexpr (PROF) ring_wait += clock64() - tr0;
     }
 
     __device__ __forceinline__ FinishArgs stage_args(const SlotDev &sl, int i, int T) const
@@ -613,6 +617,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
         for (int k = 0; k < 3; ++k) c.prof[(size_t)g * 16 + 5 + k] = pc[k];
         c.prof[(size_t)g * 16 + 14] = fin.pcc[0];
         c.prof[(size_t)g * 16 + 15] = fin.pcc[1];
+        c.prof[(size_t)g * 16 + 13] = fin.ring_wait;
     }
 #undef PROF_LAP
 }
@@ -748,7 +753,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         pc[4] = smid;  // which SM hosted this slice
-        for (int k = 0; k < 6; ++k) c.prof[(size_t)g * 16 + 8 + k] = pc[k];
+        for (int k = 0; k < 5; ++k) c.prof[(size_t)g * 16 + 8 + k] = pc[k];  // slot 13: the scatter warps' ring wait
     }
 }
 

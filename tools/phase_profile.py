@@ -31,7 +31,7 @@ def line(row):
     return ("compute: " + " ".join(f"{nm}={row[k]/stg:7.0f}" for k, nm in enumerate(names_c)) +
             " | scatter: " + " ".join(f"{nm}={row[5+k]/stg:7.0f}" for k, nm in enumerate(names_s)) +
             " (" + " ".join(f"{nm}={row[14+k]/stg:6.0f}" for k, nm in enumerate(names_x)) + ")" +
-            " | comm/stage: " + " ".join(f"{nm}={row[8+k]/stg:6.2f}" for k, nm in enumerate(names_m)))
+            f" ring_wait={row[13]/stg:6.0f}" + " | comm/stage: " + " ".join(f"{nm}={row[8+k]/stg:6.2f}" for k, nm in enumerate(names_m)))
 for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
     if 0 <= gsel < G:
         print(f"cta {gsel:3d} " + line(prof[gsel]))
