@@ -19,9 +19,7 @@
 namespace bb200 {
 
 constexpr int kChunk = 64;        // stages per TMA chunk of df / u_old
-constexpr int kWaveThreadsBig = 256;    // wavefront CTA cap for large register tiles (7 compute warps + comm): 255 regs/thread
-constexpr int kWaveThreadsMid = 384;    // small tiles with up to 12 warps: 168 regs/thread (room for a good phase-B schedule)
-constexpr int kWaveThreadsSmall = 512;  // cap for small tiles (up to 16 warps): 128 regs/thread
+constexpr int kWaveThreadsSmall = 512;  // wavefront CTA cap (up to 16 warps: compute + comm + publisher + scatter): 128 regs/thread
 constexpr int kMaxM = 8;          // controls supported by the kernels
 constexpr int kFlagStride = 16;   // u64 words between per-CTA progress flags (128 B apart)
 constexpr int kHaloRing = 32;     // stages of halo kept in flight between neighbouring CTAs (deep: a push can span many slices)

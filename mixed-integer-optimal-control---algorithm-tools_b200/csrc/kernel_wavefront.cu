@@ -32,7 +32,13 @@
 //   * Phase C (scatter): the JS partial (min, argmin) pairs of a cell are combined in ascending-j order with the
 //     same strict '>' (the earliest group holding the minimum wins).  The value goes to the next stage's rows
 //     (own slice: shared memory; higher slice: global ring), the argmin to HBM once per cell as uint8 indexed
-//     by source row (coalesced rows).
+//     by source row (coalesced rows).  Tiles with one j-group skip phase C: the thread scatters its finished
+//     cells from registers ("direct" mode).
+//   * Code size is a first-order concern: five roles run different code on one SM and the code executed every
+//     stage has to stay below the 32 KB instruction-cache tier (it was 36 KB: 95 % hit rate, 6 % slower).  Hence
+//     one out-of-line wait loop, one phase-C unit in flight per warp, +Inf pad rows in the jump-cost table (every
+//     j-group runs whole trips of the unrolled scan; remainder code stays cold), 32-bit ticks, and the cycle
+//     counters as a separate instantiation (template parameter PROF).
 #include "bb200_internal.cuh"
 #include "kernels.cuh"
 
@@ -537,20 +543,9 @@ struct Finisher {
         return a;
     }
 
-    // phase C of work units [ub, ue) of stage i (global step T)
-    __device__ __forceinline__ void rows(const SlotDev &sl, int i, int T, int ub, int ue)
+    // phase C of work units [ub, ue) of the stage described by `a` (stage_args)
+    __device__ __forceinline__ void rows(const FinishArgs &a, int ub, int ue)
     {
-        const int Kp = t.Kp, B1 = t.B1, R = c.R;
-        FinishArgs a;
-        a.pv = sm.pv;
-        a.pa = sm.pa;
-        a.bt = sm.bts + (size_t)(T % 3) * Kp;
-        a.umap = sm.umap;
-        a.Pn = sm.Ps + (size_t)((i - 1) & 1) * R * Kp;
-        a.hring = c.halo + ((size_t)(T % kHaloRing) * B1 + r0) * Kp;
-        a.phi = (i <= 2) ? sl.phi + ((size_t)((i + 1) & 1) * B1 + r0) * Kp : nullptr;
-        a.argrow = reinterpret_cast<unsigned char *>(sl.arg) + ((size_t)(i - 1) * B1 + r0) * Kp * sizeof(ArgT);
-        a.JS = c.JS; a.R = R; a.Kp = Kp; a.K = t.K; a.B1 = B1; a.r0 = r0;
         long long *pccp = (PROF && c.prof) ? pcc : nullptr;
 #ifdef BB_EXP_SMALL
         finish_rows<4, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp);
@@ -598,6 +593,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
         ++T;
         for (int i = n - 1; i >= 1; --i, ++T) {
             wait_costs(T);
+            const FinishArgs fa = fin.stage_args(sl, i, T);  // once per stage, shared by both sub-slices
             for (int v = 0; v < NV; ++v) {
                 mbar_wait_wd(&sm.mbar[MB_SCANNED + v], (scanned_phase >> v) & 1u, c.err);
                 scanned_phase ^= 1u << v;
@@ -607,7 +603,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
                     PROF_LAP(1);
                 }
                 const int ub = v == 0 ? 0 : c.RA * ublocks, ue = v == 0 ? c.RA * ublocks : R * ublocks;
-                if (c.decouple < 2) fin.rows(sl, i, T, ub, ue);
+                if (c.decouple < 2) fin.rows(fa, ub, ue);
                 finished(v);
                 PROF_LAP(2);
             }
@@ -929,7 +925,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 scanned_phase ^= 1u;
                 fin.wait_inputs(i, T);
                 PROF_LAP(2);
-                fin.rows(sl, i, T, 0, R * fin.ublocks);
+                fin.rows(fin.stage_args(sl, i, T), 0, R * fin.ublocks);
                 finished();
                 PROF_LAP(3);
             }
