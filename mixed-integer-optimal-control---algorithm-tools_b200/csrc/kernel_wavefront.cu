@@ -594,14 +594,14 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
         for (int i = n - 1; i >= 1; --i, ++T) {
             wait_costs(T);
             const FinishArgs fa = fin.stage_args(sl, i, T);  // once per stage, shared by both sub-slices
+            // everything that does not need the scan happens while the compute warps are still scanning sub-slice A:
+            // the halo rows of this stage have landed, the ring slot is free
+            fin.wait_inputs(i, T);
+            PROF_LAP(1);
             for (int v = 0; v < NV; ++v) {
                 mbar_wait_wd(&sm.mbar[MB_SCANNED + v], (scanned_phase >> v) & 1u, c.err);
                 scanned_phase ^= 1u << v;
                 PROF_LAP(0);
-                if (v == 0) {
-                    fin.wait_inputs(i, T);
-                    PROF_LAP(1);
-                }
                 const int ub = v == 0 ? 0 : c.RA * ublocks, ue = v == 0 ? c.RA * ublocks : R * ublocks;
                 if (c.decouple < 2) fin.rows(fa, ub, ue);
                 finished(v);
