@@ -133,7 +133,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
 #define BB_UNROLL 4
 #endif
 #ifndef BB_CU
-#define BB_CU 1
+#define BB_CU 1  /* unused since phase C walks its units one at a time */
 #endif
 constexpr int kUnrollB = BB_UNROLL;  // successor pairs per trip of the phase-B loop
 constexpr int kNever = 0x7fffffff;  // "no bound": ticks are 32-bit, wave_configure refuses launches with >= 2^30 steps
@@ -213,11 +213,7 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 #pragma unroll
     for (int q = 0; q < TL; ++q) s[q] = srow[q];
     // main loop: full pairs, one straight-line block so that the two candidates' chains interleave
-#ifdef BB_EXP_SMALL
-    const int je2 = jb + 32;  // EXPERIMENT ONLY: config 4 with four j-groups (pad columns/rows hold +Inf)
-#else
     const int je2 = jb + ((je - jb) & ~1);
-#endif
 #pragma unroll kUnrollB
     for (int j = jb; j < je2; j += 2) {
         double p0[TB], p1[TB];
@@ -262,7 +258,6 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
             }
         }
     }
-#ifndef BB_EXP_SMALL
     if (je2 < je) {  // odd tail: one last successor
         const int j = je2;
 #pragma unroll
@@ -275,7 +270,6 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
             }
         }
     }
-#endif
 }
 
 // scan + partial (min, argmin) of this thread's j-group into shared memory for phase C
@@ -309,17 +303,18 @@ struct FinishArgs {
     int JS, R, Kp, K, B1, r0;
 };
 
-// Finishes `CU` work units at once so that the dependent load -> compare -> select chains of different cells
-// overlap.  A unit is 64 consecutive levels of one source row; a lane owns two neighbouring cells and fetches
-// their partial minima with one 16-byte load per j-group (and both argmins with one 2-byte load).  Units [ub, ue)
-// of the CTA belong to the sub-slice being finished; warp sw of NS takes every NS-th one.
-template <int JSC, typename ArgT, bool PROF>
+// Finishes the work units [ub, ue) of a sub-slice; warp sw of NS takes every NS-th one.  A unit is 32 * EC
+// consecutive levels of one source row: a lane owns EC neighbouring cells and fetches their partial minima with
+// 16-byte loads (EC / 2 per j-group) and all EC argmins with one load.  Phase C is latency bound, so what counts is
+// the number of units a warp has to walk through one after the other: EC = 4 (a whole 128-level row per unit) when
+// that gives every scatter warp at most one unit of a sub-slice, EC = 2 otherwise.
+template <int JSC, int EC, typename ArgT, bool PROF>
 __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue, int sw, int NS, int lane, long long *pcc)
 {
-    static_assert(sizeof(ArgT) == 1, "the packed two-cell argmin load assumes one byte per cell");
+    static_assert(sizeof(ArgT) == 1, "the packed argmin load assumes one byte per cell");
+    static_assert(EC == 2 || EC == 4, "two or four cells per lane");
     long long tq0 = 0;
     if constexpr (PROF) tq0 = pcc ? clock64() : 0;
-    constexpr int CU = BB_CU;  // units in flight per warp: 1 keeps the code small (instruction cache), see DESIGN.md
     const double inf = d_inf();
     const double *__restrict__ pv = a.pv;
     const unsigned char *__restrict__ pa = a.pa;
@@ -330,102 +325,95 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
     double *__restrict__ hring = a.hring;
     const int RK = a.R * a.Kp;
     const int rows_left = a.B1 - a.r0;  // rows of this slice that exist in the table
-    for (int u0 = ub + sw; u0 < ue; u0 += NS * CU) {
-        double val[CU][2];
-        int arg[CU][2], x_[CU], y_[CU][2];
-        bool no_src[CU][2], ok[CU][2];
-#pragma unroll
-        for (int u = 0; u < CU; ++u) {
-            const int unit = u0 + u * NS;
-            const bool live = unit < ue;
-            const int m = umap[live ? unit : ub];
-            const int row = m >> 16;
-            const int l0 = min((m & 0xffff) + 2 * lane, a.Kp - 2);  // a half-filled last unit re-reads the last pair
-            const bool lane_live = live && (m & 0xffff) + 2 * lane < a.Kp;
-            const int2 bt = *reinterpret_cast<const int2 *>(btp + l0);
-            x_[u] = row * a.Kp + l0;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int bte = e ? bt.y : bt.x;
-                const bool in_tab = lane_live && l0 + e < a.K && row < rows_left;
-                y_[u][e] = x_[u] + e + bte * a.Kp;  // (target row - r0) * Kp + l
-                // target cell (bsrc, l) of my rows has no source row when bsrc < b~_l: +Inf (:47).  This also covers
-                // levels that are unreachable at this stage (b~ clamped to B1).
-                no_src[u][e] = in_tab && a.r0 + row < bte;
-                // cells outside `for b = 0:B-b~` (:69) are not computed by the reference either
-                ok[u][e] = in_tab && row + bte < rows_left;
-            }
+#pragma unroll 1
+    for (int unit = ub + sw; unit < ue; unit += NS) {
+        const int m = umap[unit];
+        const int row = m >> 16;
+        const int l0 = min((m & 0xffff) + EC * lane, a.Kp - EC);  // a partly filled last unit re-reads the last cells
+        const bool lane_live = (m & 0xffff) + EC * lane < a.Kp;
+        const int x = row * a.Kp + l0;
+        int bt[EC];
+        if constexpr (EC == 4) {
+            const int4 b4 = *reinterpret_cast<const int4 *>(btp + l0);
+            bt[0] = b4.x; bt[1] = b4.y; bt[2] = b4.z; bt[3] = b4.w;
+        } else {
+            const int2 b2 = *reinterpret_cast<const int2 *>(btp + l0);
+            bt[0] = b2.x; bt[1] = b2.y;
         }
+        double val[EC];
+        int arg[EC], y[EC];
+        bool no_src[EC], ok[EC];
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+            const bool in_tab = lane_live && l0 + e < a.K && row < rows_left;
+            y[e] = x + e + bt[e] * a.Kp;  // (target row - r0) * Kp + l
+            // target cell (bsrc, l) of my rows has no source row when bsrc < b~_l: +Inf (:47).  This also covers
+            // levels that are unreachable at this stage (b~ clamped to B1).
+            no_src[e] = in_tab && a.r0 + row < bt[e];
+            // cells outside `for b = 0:B-b~` (:69) are not computed by the reference either
+            ok[e] = in_tab && row + bt[e] < rows_left;
+        }
+        auto load = [&](int q, double (&v)[EC], unsigned int &g) {
+#pragma unroll
+            for (int h = 0; h < EC / 2; ++h) {
+                const double2 w = *reinterpret_cast<const double2 *>(pv + q * RK + x + 2 * h);
+                v[2 * h] = w.x;
+                v[2 * h + 1] = w.y;
+            }
+            if constexpr (EC == 4) g = *reinterpret_cast<const unsigned int *>(pa + q * RK + x);
+            else g = (unsigned int)*reinterpret_cast<const unsigned short *>(pa + q * RK + x);
+        };
+        unsigned int gsel[EC];  // the packed argmins of the group that currently wins cell e
         if constexpr (JSC > 0) {
             // all partial (min, argmin) pairs are loaded before the first compare; tournament in ascending group order,
             // on ties the earlier group stays (strict '>', HelpFunctions.jl:73).  Partial minima are never NaN and
             // carry MARK with +Inf, so this equals the sequential scan.
-            double v[CU][JSC][2];
-            int g[CU][JSC];  // both cells' argmins, packed
+            double v[JSC][EC];
+            unsigned int g[JSC];
 #pragma unroll
-            for (int u = 0; u < CU; ++u)
+            for (int q = 0; q < JSC; ++q) load(q, v[q], g[q]);
+            unsigned int gw[JSC][EC];
 #pragma unroll
-                for (int q = 0; q < JSC; ++q) {
-                    const double2 w = *reinterpret_cast<const double2 *>(pv + q * RK + x_[u]);
-                    v[u][q][0] = w.x;
-                    v[u][q][1] = w.y;
-                    g[u][q] = (int)*reinterpret_cast<const unsigned short *>(pa + q * RK + x_[u]);
-                }
-            int gw[CU][JSC][2];
+            for (int q = 0; q < JSC; ++q)
 #pragma unroll
-            for (int u = 0; u < CU; ++u)
-#pragma unroll
-                for (int q = 0; q < JSC; ++q) { gw[u][q][0] = g[u][q]; gw[u][q][1] = g[u][q]; }
+                for (int e = 0; e < EC; ++e) gw[q][e] = g[q];
 #pragma unroll
             for (int w = 1; w < JSC; w *= 2)
 #pragma unroll
                 for (int q = 0; q + w < JSC; q += 2 * w)
 #pragma unroll
-                    for (int u = 0; u < CU; ++u)
+                    for (int e = 0; e < EC; ++e)
+                        if (v[q][e] > v[q + w][e]) { v[q][e] = v[q + w][e]; gw[q][e] = gw[q + w][e]; }
 #pragma unroll
-                        for (int e = 0; e < 2; ++e)
-                            if (v[u][q][e] > v[u][q + w][e]) { v[u][q][e] = v[u][q + w][e]; gw[u][q][e] = gw[u][q + w][e]; }
-#pragma unroll
-            for (int u = 0; u < CU; ++u) {
-                val[u][0] = v[u][0][0];
-                val[u][1] = v[u][0][1];
-                arg[u][0] = gw[u][0][0] & 0xff;
-                arg[u][1] = gw[u][0][1] >> 8;
-            }
+            for (int e = 0; e < EC; ++e) { val[e] = v[0][e]; gsel[e] = gw[0][e]; }
         } else {
             // any other split: sequential scan over the groups
-            int gw[CU][2];
 #pragma unroll
-            for (int u = 0; u < CU; ++u) { val[u][0] = inf; val[u][1] = inf; gw[u][0] = 0xffff; gw[u][1] = 0xffff; }
+            for (int e = 0; e < EC; ++e) { val[e] = inf; gsel[e] = 0xffffffffu; }
 #pragma unroll 1
             for (int q = 0; q < a.JS; ++q) {
+                double v[EC];
+                unsigned int g;
+                load(q, v, g);
 #pragma unroll
-                for (int u = 0; u < CU; ++u) {
-                    const double2 w = *reinterpret_cast<const double2 *>(pv + q * RK + x_[u]);
-                    const int g = (int)*reinterpret_cast<const unsigned short *>(pa + q * RK + x_[u]);
-                    if (val[u][0] > w.x) { val[u][0] = w.x; gw[u][0] = g; }  // strict: earliest group wins ties
-                    if (val[u][1] > w.y) { val[u][1] = w.y; gw[u][1] = g; }
-                }
+                for (int e = 0; e < EC; ++e)
+                    if (val[e] > v[e]) { val[e] = v[e]; gsel[e] = g; }  // strict: earliest group wins ties
             }
-#pragma unroll
-            for (int u = 0; u < CU; ++u) { arg[u][0] = gw[u][0] & 0xff; arg[u][1] = gw[u][1] >> 8; }
         }
+#pragma unroll
+        for (int e = 0; e < EC; ++e) arg[e] = (int)((gsel[e] >> (8 * e)) & 0xffu);
         if constexpr (PROF) { if (pcc) { const long long tq = clock64(); pcc[0] += tq - tq0; tq0 = tq; } }
 #pragma unroll
-        for (int u = 0; u < CU; ++u)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if (no_src[u][e]) Pn[x_[u] + e] = inf;
-                if (ok[u][e]) argrow[x_[u] + e] = (unsigned char)arg[u][e];
-                if (ok[u][e] && y_[u][e] < RK) Pn[y_[u][e]] = val[u][e];
-                if (ok[u][e] && y_[u][e] >= RK) hring[y_[u][e]] = val[u][e];
-            }
+        for (int e = 0; e < EC; ++e) {
+            if (no_src[e]) Pn[x + e] = inf;
+            if (ok[e]) argrow[x + e] = (unsigned char)arg[e];
+            if (ok[e] && y[e] < RK) Pn[y[e]] = val[e];
+            if (ok[e] && y[e] >= RK) hring[y[e]] = val[e];
+        }
         if (a.phi) {  // stages 2 and 1 are the exit state (S7)
 #pragma unroll
-            for (int u = 0; u < CU; ++u)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    if (ok[u][e]) a.phi[y_[u][e]] = val[u][e];
+            for (int e = 0; e < EC; ++e)
+                if (ok[e]) a.phi[y[e]] = val[e];
         }
         if constexpr (PROF) { if (pcc) { const long long tq = clock64(); pcc[1] += tq - tq0; tq0 = tq; } }
     }
@@ -471,14 +459,14 @@ struct Finisher {
     const Smem &sm;
     const int fw, NF, lane;  // this warp's index among the NF finisher warps
     const int r0, lblocks;  // 32-level blocks per row (terminal stage)
-    const int ublocks;      // 64-level work units per row (phase C)
+    const int ublocks;      // work units (32 * EC levels) per row (phase C)
     bool halo_on, pushes;
     uint32_t halo_phase = 0;
     long long pcc[2] = {0, 0};  // profile: loads + combine, stores
     long long ring_wait = 0;    // profile: cycles spent waiting for ring space
 
     __device__ __forceinline__ Finisher(const Tables &t_, const WaveCfg &c_, const Smem &sm_, int fw_, int NF_, int lane_)
-        : t(t_), c(c_), sm(sm_), fw(fw_), NF(NF_), lane(lane_), r0(blockIdx.x * c_.R), lblocks(t_.Kp >> 5), ublocks((t_.Kp + 63) >> 6)
+        : t(t_), c(c_), sm(sm_), fw(fw_), NF(NF_), lane(lane_), r0(blockIdx.x * c_.R), lblocks(t_.Kp >> 5), ublocks((t_.Kp + 32 * c_.EC - 1) / (32 * c_.EC))
     {
         const int btm = min(*c.btmax, t.B1 - 1);
         halo_on = (blockIdx.x > 0 && btm > 0);  // lower slices push into this one
@@ -547,15 +535,13 @@ struct Finisher {
     __device__ __forceinline__ void rows(const FinishArgs &a, int ub, int ue)
     {
         long long *pccp = (PROF && c.prof) ? pcc : nullptr;
-#ifdef BB_EXP_SMALL
-        finish_rows<4, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp);
-#else
+        // EC = 4 (a whole 128-level row per unit, one unit per scatter warp) was measured too: the finishing pass of
+        // sub-slice A gets shorter (3 500 -> 2 400 cycles) but its larger code slows the scan by more (profiles/README.md)
         switch (c.JS) {
-            case 2: finish_rows<2, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
-            case 4: finish_rows<4, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
-            default: finish_rows<0, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
+            case 2: finish_rows<2, 2, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
+            case 4: finish_rows<4, 2, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
+            default: finish_rows<0, 2, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
         }
-#endif
     }
 };
 
@@ -798,8 +784,10 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     // one-time: jump costs into shared memory, value rows to +Inf, barriers and counters
     for (int x = tid; x < c.Kr * Kp; x += blockDim.x) sm.cs[x] = x < K * Kp ? t.cost[x] : inf;  // pad rows: never win
     for (int x = tid; x < 2 * R * Kp; x += blockDim.x) sm.Ps[x] = inf;
-    for (int x = tid; x < R * ((Kp + 63) >> 6); x += blockDim.x)
-        sm.umap[x] = ((x / ((Kp + 63) >> 6)) << 16) | ((x % ((Kp + 63) >> 6)) << 6);
+    {
+        const int ul = 32 * c.EC, ubl = (Kp + ul - 1) / ul;  // levels per phase-C work unit, units per row
+        for (int x = tid; x < R * ubl; x += blockDim.x) sm.umap[x] = ((x / ubl) << 16) | ((x % ubl) * ul);
+    }
     if (tid == 0) {
         for (int k = 0; k < 5; ++k) mbar_init(&sm.mbar[k], 1);  // cost[3], halo[2]: one arming arrival + tx bytes
         for (int v = 0; v < 2; ++v) {
@@ -993,6 +981,7 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int N
     }
     c.tpg = ((c.RG * c.nLG + 31) / 32) * 32;
     c.NS = NS;
+    c.EC = 2;  // cells per lane in phase C (the kernel dispatches EC = 2 only, see Finisher::rows)
     c.NF = c.NS > 0 ? c.NS : c.JS * c.tpg / 32;  // warps that finish a stage: scatter warps, else the compute warps
     c.threads = c.JS * c.tpg + 64 + 32 * c.NS;  // + comm warp + publisher warp + scatter warps
     c.smem = carve(t, c, argw, nullptr, nullptr);
@@ -1047,10 +1036,10 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 // scan only get the issue slots it leaves (constants fitted to tools/tune_sweep.py runs of the
                 // config-4 and the heat-shaped instance, profiles/tune_sweep*_r01.txt)
                 auto finish = [&](int rows, bool hidden) {
-                    const int units = rows * ((t.Kp + 63) / 64);
+                    const int units = rows * ((t.Kp + 32 * c.EC - 1) / (32 * c.EC));
                     const int per_warp = (units + c.NF - 1) / c.NF;
                     const double generic = (js == 2 || js == 4) ? 1.0 : 1.5;  // other splits: rolled combine loop
-                    return per_warp * generic * (hidden ? 1200.0 + 50.0 * js : 100.0 + 310.0 * js) + 300.0;
+                    return per_warp * generic * (c.EC == 4 ? 1.4 : 1.0) * (hidden ? 1200.0 + 50.0 * js : 100.0 + 310.0 * js) + 300.0;
                 };
                 const double sa = scan(c.TB), sb = scan(c.TBB);
                 double stage;

@@ -30,6 +30,7 @@ struct WaveCfg {
     int tpg;      // threads per group (multiple of 32)
     int NS;       // scatter warps (phase C); 0 when the tile has one sub-slice and the compute warps finish it
     int NF;       // warps that finish a stage: NS, or the compute warps
+    int EC;       // cells per lane in phase C (2 or 4): a work unit is 32 * EC levels of one row
     int threads;  // JS * tpg compute threads + comm warp + publisher warp + NS scatter warps
     size_t smem;  // dynamic shared memory bytes
     int nsub;     // subproblems walked by this launch
