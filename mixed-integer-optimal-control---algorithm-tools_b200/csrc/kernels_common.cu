@@ -316,9 +316,8 @@ __global__ void select_kernel(Tables t, SlotDev slot, int Bnew_arg, const int *b
 // window is reloaded around the actual budget.
 // ------------------------------------------------------------------------------------------------
 template <typename ArgT>
-__global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev slot, int *err, int S, int W)
+__global__ void __launch_bounds__(256, 1) backtrack_kernel(Tables t, SlotDev slot, int *err, int S, int W)
 {
-    constexpr ArgT MARK = (ArgT)~(ArgT)0;
     extern __shared__ __align__(128) unsigned char smem_bt[];
     const int Kp = t.Kp;
     const uint32_t win_bytes = (uint32_t)(((size_t)S * W * Kp * sizeof(ArgT) + 127) / 128 * 128);
@@ -348,16 +347,17 @@ __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev sl
         int wb = top - W + 1;
         if (wb < 0) wb = 0;
         const int wrows = min(W, t.B1 - wb);
-        if (tid < 32) {
+        if (tid >= 32 && tid < 64) {  // warp 1 issues: warp 0 hosts the chase thread and must not be delayed
+            const int ln = tid - 32;
             unsigned char *base = smem_bt + (size_t)k * buf_bytes;
             const uint32_t wbytes = (uint32_t)((size_t)wrows * Kp * sizeof(ArgT));
-            if (tid == 0)
+            if (ln == 0)
                 mbar_expect_tx(&s_bar[k], (uint32_t)cnt * wbytes + (uint32_t)((size_t)cnt * Kp * sizeof(int)));
             __syncwarp();
-            for (int st = tid; st < cnt; st += 32)
+            for (int st = ln; st < cnt; st += 32)
                 tma_load_1d(base + (size_t)st * W * Kp * sizeof(ArgT), arg + ((size_t)(i0 + st - 1) * t.B1 + wb) * Kp, wbytes,
                             &s_bar[k]);
-            if (tid == 0)
+            if (ln == 0)
                 tma_load_1d(base + win_bytes, slot.bt_all + (size_t)(i0 - 1) * Kp, (uint32_t)((size_t)cnt * Kp * sizeof(int)),
                             &s_bar[k]);
         }
@@ -406,12 +406,16 @@ __global__ void __launch_bounds__(1024, 1) backtrack_kernel(Tables t, SlotDev sl
             int b = b0, l = s_l, st = 0, fail = 0;
             for (; st < cnt; ++st, wn += WK, bt += Kp) {
                 const int bsrc = b - bt[l];
-                if (bsrc < 0) { fail = 1; break; }     // unreachable level: the reference would read stale U
-                if (bsrc < wb && st > 0) break;        // left the window: re-centre
-                // (a first step that jumps below the window reads its one entry straight from HBM)
-                const ArgT a = (bsrc >= wb) ? wn[(bsrc - wb) * Kp + l]
-                                            : arg[((size_t)(i0 + st - 1) * t.B1 + bsrc) * Kp + l];
-                if (a == MARK || (int)a >= t.K) { fail = 1; break; }
+                ArgT a;
+                if (bsrc >= wb) {                      // the common case: one branch, two dependent shared-memory loads
+                    a = wn[(bsrc - wb) * Kp + l];
+                } else {
+                    if (bsrc < 0) { fail = 1; break; }  // unreachable level: the reference would read stale U
+                    if (st > 0) break;                  // left the window: re-centre
+                    // a first step that jumps below the window reads its one entry straight from HBM
+                    a = arg[((size_t)(i0 + st - 1) * t.B1 + bsrc) * Kp + l];
+                }
+                if ((int)a >= t.K) { fail = 1; break; }  // MARK (all ones) or garbage: no candidate won this cell
                 l = (int)a;
                 b = bsrc;
                 lseq[st] = l;
@@ -563,10 +567,10 @@ void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, 
     const size_t smem = 2 * (win_bytes + (size_t)S * t.Kp * sizeof(int)) + (size_t)S * sizeof(int) + 128;
     if (argw == 1) {
         cudaFuncSetAttribute(backtrack_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        backtrack_kernel<uint8_t><<<1, 1024, smem, st>>>(t, slot, err, (int)S, W);
+        backtrack_kernel<uint8_t><<<1, 256, smem, st>>>(t, slot, err, (int)S, W);
     } else {
         cudaFuncSetAttribute(backtrack_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        backtrack_kernel<uint16_t><<<1, 1024, smem, st>>>(t, slot, err, (int)S, W);
+        backtrack_kernel<uint16_t><<<1, 256, smem, st>>>(t, slot, err, (int)S, W);
     }
 }
 
