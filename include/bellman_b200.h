@@ -188,6 +188,16 @@ int bb200_profile(bb200_plan *plan, int32_t enable, int64_t *out, int32_t max_ct
  * wavefront kernel's tile table; add 100 * NS to force NS scatter warps per CTA). */
 int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t variant);
 
+/* The geometry the persistent wavefront kernel would pick for a table shape on a GPU with `num_sms` SMs and
+ * `smem_max` bytes of opt-in shared memory per CTA.  Pure host code (no CUDA call): it lets CPU-only tests pin the
+ * geometry model.  ctas / jsplit / variant as in bb200_plan_tune.  out (values beyond `count` are not written):
+ *   0 1 if the shape runs on the wavefront kernel, else 0      1 tile variant (1-based)
+ *   2 rows per thread tile in sub-slice A   3 in sub-slice B (0: one sub-slice)   4 levels per thread tile
+ *   5 CTAs   6 source rows per CTA   7 j-split   8 successors per j-group   9 rows of the padded jump-cost table
+ *  10 scatter warps   11 threads per CTA   12 dynamic shared memory per CTA [bytes] */
+int bb200_wave_geometry(int64_t n, int32_t M, int32_t K, int64_t B, int32_t num_sms, int64_t smem_max, int32_t ctas,
+                        int32_t jsplit, int32_t variant, int64_t *out, int32_t count);
+
 #ifdef __cplusplus
 }
 #endif

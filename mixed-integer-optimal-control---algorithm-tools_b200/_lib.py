@@ -29,6 +29,8 @@ SIGNATURES = {
     "bb200_plan_destroy": (ctypes.c_int, [c_plan_p]),
     "bb200_plan_set_stream": (ctypes.c_int, [c_plan_p, ctypes.c_void_p]),
     "bb200_plan_tune": (ctypes.c_int, [c_plan_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
+    "bb200_wave_geometry": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
+                                           ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _I64P, ctypes.c_int32]),
     "bb200_bellman": (ctypes.c_int, [c_plan_p, _F64P, _F64P]),
     "bb200_select_and_backtrack": (ctypes.c_int, [c_plan_p, ctypes.c_int64, _F64P, _F64P, _I64P, _I64P]),
     "bb200_solve": (ctypes.c_int, [c_plan_p, _F64P, _F64P, ctypes.c_int64, _F64P, _F64P, _I64P, _I64P]),

@@ -481,6 +481,20 @@ int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t vari
     return BB200_OK;
 }
 
+int bb200_wave_geometry(int64_t n, int32_t M, int32_t K, int64_t B, int32_t num_sms, int64_t smem_max, int32_t ctas,
+                        int32_t jsplit, int32_t variant, int64_t *out, int32_t count)
+{
+    if (!out || n < 1 || M < 1 || K < 1 || B < 0 || num_sms < 1 || smem_max < 0) return fail(BB200_ERR_ARG, "bad arguments");
+    Tables t{};
+    t.n = (int)n; t.M = M; t.K = K; t.Kp = (K + 31) / 32 * 32; t.B1 = (int)B + 1; t.dt = 1.0;
+    WaveCfg c{};
+    const bool ok = wave_configure(t, K <= 255 ? 1 : 2, num_sms, (size_t)smem_max, ctas, jsplit, variant, c);
+    const int64_t v[13] = {ok ? 1 : 0, ok ? c.variant + 1 : 0, c.TB, c.TBB, c.TL, c.G, c.R, c.JS, c.jper, c.Kr, c.NS,
+                           c.threads, (int64_t)c.smem};
+    for (int k = 0; k < count && k < 13; ++k) out[k] = ok || k == 0 ? v[k] : 0;
+    return BB200_OK;
+}
+
 int bb200_upload(bb200_plan *plan, int32_t slot, const double *df, const double *u_old)
 {
     int rc = check_slot(plan, slot);
