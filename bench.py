@@ -135,6 +135,10 @@ def run_reference(args):
     """The reference arm: the CPU implementation of the path on the host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for every rank; the other ranks have just exited, so rank 0 takes all host cores
+    # (set before the OpenMP runtime is loaded with the oracle library)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import oracle as o
     o.build()
     m = importlib.import_module("mioc_b200")
