@@ -1025,8 +1025,8 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 const int cwarps = c.JS * c.tpg / 32;
                 const int sched = (cwarps + 3) / 4;
                 // one warp per scheduler cannot hide the compare -> select latency; three or more run with 128
-                // registers and a longer schedule (measured: 1.5 / 1.3 / 1.4)
-                const double stall = sched == 1 ? 1.5 : sched == 2 ? 1.3 : 1.4;
+                // registers and a longer schedule (measured: 1.65 / 1.3 / 1.4)
+                const double stall = sched == 1 ? 1.65 : sched == 2 ? 1.3 : 1.4;
                 auto scan = [&](int tb) {
                     if (tb == 0) return 0.0;
                     const double per_j = 7.0 * tb * c.TL + 2.0 * c.TL + ((tb + 1) / 2) + ((c.TL + 1) / 2) + 3.0;
