@@ -135,6 +135,15 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
 #ifndef BB_CU
 #define BB_CU 1  /* unused since phase C walks its units one at a time */
 #endif
+// An empty volatile asm inside the update keeps the front end from turning `if (best > v) { best = v; arg = j; }`
+// into selects (DSETP + FSEL + FSEL + SEL: three instructions on the half-rate ALU pipe, which then binds the scan).
+// ptxas if-converts the short branch itself into three PREDICATED MOVES and spreads them over the ALU and the FMA
+// pipe (@P MOV / @P IMAD.MOV.U32), profiles/scan_probe_r02.txt.
+#ifndef BB_SELECT_UPDATE
+#define BB_KEEP_BRANCH asm volatile("")
+#else
+#define BB_KEEP_BRANCH
+#endif
 constexpr int kUnrollB = BB_UNROLL;  // successor pairs per trip of the phase-B loop
 constexpr int kNever = 0x7fffffff;  // "no bound": ticks are 32-bit, wave_configure refuses launches with >= 2^30 steps
 
@@ -246,7 +255,7 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 #pragma unroll
             for (int r = 0; r < TB; ++r) {
                 const double v = __dadd_rn(a0[q], p0[r]);               // :71
-                if (best[r][q] > v) { best[r][q] = v; arg[r][q] = j; }  // :73-76, strict: the earliest j wins
+                if (best[r][q] > v) { BB_KEEP_BRANCH; best[r][q] = v; arg[r][q] = j; }  // :73-76, strict: the earliest j wins
             }
         }
 #pragma unroll
@@ -254,7 +263,7 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 #pragma unroll
             for (int r = 0; r < TB; ++r) {
                 const double v = __dadd_rn(a1[q], p1[r]);
-                if (best[r][q] > v) { best[r][q] = v; arg[r][q] = j + 1; }
+                if (best[r][q] > v) { BB_KEEP_BRANCH; best[r][q] = v; arg[r][q] = j + 1; }
             }
         }
     }
@@ -266,7 +275,7 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 #pragma unroll
             for (int r = 0; r < TB; ++r) {
                 const double v = __dadd_rn(a, Prow[(size_t)r * Kp + j]);
-                if (best[r][q] > v) { best[r][q] = v; arg[r][q] = j; }
+                if (best[r][q] > v) { BB_KEEP_BRANCH; best[r][q] = v; arg[r][q] = j; }
             }
         }
     }
