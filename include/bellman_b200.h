@@ -51,6 +51,8 @@ extern "C" {
 #define BB200_FLAG_FORCE_WAVEFRONT 4u /* never use the single-CTA small-problem kernel (tests)       */
 
 typedef struct bb200_plan bb200_plan;
+typedef struct bb200_comm bb200_comm;   /* one rank of an NCCL communicator (one process per GPU)  */
+typedef struct bb200_multi bb200_multi; /* all GPUs of one process: one plan + host thread per GPU */
 
 const char *bb200_last_error(void);
 /* Library/ABI version (major*1000+minor). */
@@ -107,20 +109,71 @@ int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t
                 double *u_out, double *phi_star, int64_t *b_star, int64_t *k_star);
 
 /* Batched variants: S independent subproblems (own df, u_old) sharing the plan's tables, processed in
- * waves of `batch` slots.  df_all/u_old_all: double[S][n][M].  For every subproblem, n_radii
+ * waves of `batch` slots.  df_all/u_old_all: double[S][n][M].  For every subproblem, n_radii (<= 16)
  * selections/backtracks are taken from its one table (a radius sweep costs one DP, multi-trust.jl:109-110):
  *   u_out_all       double[S][n_radii][n][M]   (may be NULL: only the optima are returned)
  *   phi_star/b_star/k_star   [S][n_radii]       (each may be NULL)
+ *   status          int32[S][n_radii]: BB200_OK, BB200_ERR_INEXACT (that subproblem's u_old) or BB200_ERR_STALE
+ *                   (that selection), per entry; may be NULL.  The return value is the worst of them (the
+ *                   other entries are valid) or a hard error.
+ * Pipeline: the DP of a wave is one persistent launch; its selections and backtracks are ONE launch each with
+ * a CTA per (slot, radius); inputs of wave w+1 and outputs of wave w-1 move on a second stream / through
+ * pinned staging while wave w computes; the host waits once per wave.
  */
 int bb200_solve_batched(bb200_plan *plan, int64_t S, const double *df_all, const double *u_old_all,
                         int32_t n_radii, const int64_t *B_new, double *u_out_all, double *phi_star,
-                        int64_t *b_star, int64_t *k_star);
+                        int64_t *b_star, int64_t *k_star, int32_t *status);
+/* The same for the shard {first, first+stride, ...} < S of the caller's arrays (indices stay global): what one
+ * GPU of several does (subproblem s -> rank s mod G). */
+int bb200_solve_batched_shard(bb200_plan *plan, int64_t S, int64_t first, int64_t stride, const double *df_all,
+                              const double *u_old_all, int32_t n_radii, const int64_t *B_new, double *u_out_all,
+                              double *phi_star, int64_t *b_star, int64_t *k_star, int32_t *status);
 
-/* Deterministic best-candidate reduction over gathered (value, global index) records: smallest
- * value wins, ties go to the smallest index; NaN never wins against a number.  Used after the
- * per-rank records were exchanged (ncclAllGather / torch.distributed.all_gather). */
+/* Deterministic best-candidate reduction over gathered (value, global index) records in Julia's findmin
+ * order, like the selection (S8): the smallest value wins, NaN precedes every number, -0.0 precedes +0.0, equal
+ * values go to the smallest index.  Used after the per-rank records were exchanged (ncclAllGather). */
 int bb200_best_candidate(const double *values, const int64_t *indices, int64_t count,
                          double *best_value, int64_t *best_index);
+
+/* ---- multi-GPU ------------------------------------------------------------------------
+ * One DP is sequential in time, so one subproblem lives on one GPU; S independent subproblems (multi-start
+ * x0, each with its radius sweep) are sharded s -> rank s mod G with no data-path collective.  The one
+ * exchange is the best-candidate reduction: a 16-byte (value, global index) record per rank through
+ * ncclAllGather over NVLink/NVSwitch + bb200_best_candidate on every rank (NCCL has no MINLOC).  NCCL is
+ * loaded at run time (libnccl.so.2, or $BELLMAN_B200_NCCL); without it these entry points return
+ * BB200_ERR_STATE.  bb200_nccl_version() is 0 then.
+ *
+ * (a) all GPUs of ONE process -- what a Julia session uses: one ccall drives every GPU of the box. */
+int bb200_nccl_version(void);
+int bb200_multi_create(const int32_t *devices, int32_t n_dev, int64_t n, int32_t M, int32_t K, int64_t B,
+                       const int64_t *grid_dims, const int32_t *level_values, const int64_t *grid_offset,
+                       const double *jump_cost, double dt, int32_t batch_per_device, uint32_t flags,
+                       bb200_multi **out);
+int bb200_multi_destroy(bb200_multi *m);
+/* Arguments as bb200_solve_batched (all arrays global, [S]...), plus the reduction's result:
+ *   best_value, best_subproblem, best_radius   smallest selected value over all entries with status OK (Julia
+ *                   findmin order; ties -> smallest (subproblem, radius)); -1 indices if there is none
+ *   u_best          double[n][M], the winner's trajectory; taken from u_out_all or, if that is NULL, recomputed
+ *                   by one more DP of the winning subproblem on its device.  Each may be NULL. */
+int bb200_multi_solve_batched(bb200_multi *m, int64_t S, const double *df_all, const double *u_old_all,
+                              int32_t n_radii, const int64_t *B_new, double *u_out_all, double *phi_star,
+                              int64_t *b_star, int64_t *k_star, int32_t *status, double *best_value,
+                              int64_t *best_subproblem, int32_t *best_radius, double *u_best);
+/* out[0] = devices, out[1] = host wall time [ms] of the last call, out[2+d] = device time [ms] of device d's shard */
+int bb200_multi_stats(bb200_multi *m, double *out, int32_t count);
+
+/* (b) one process per GPU (torchrun, MPI, Julia Distributed): rank 0 draws the 128-byte NCCL unique id, the host
+ * program ships it to the other ranks by whatever channel it has, every rank creates its communicator. */
+int bb200_comm_unique_id(void *id128);
+int bb200_comm_create(int device, int32_t nranks, int32_t rank, const void *id128, bb200_comm **out);
+int bb200_comm_destroy(bb200_comm *comm);
+/* Collective: every rank passes its local best (value, global index < 2^53); every rank receives the global
+ * best and the rank that contributed it. */
+int bb200_comm_best_candidate(bb200_comm *comm, double value, int64_t index, double *best_value,
+                              int64_t *best_index, int32_t *owner_rank);
+/* Collective: `count` doubles from rank `root`'s host_buf to every rank's host_buf (the winner's u, n*M*8
+ * bytes) by ncclBroadcast. */
+int bb200_comm_broadcast(bb200_comm *comm, int32_t root, double *host_buf, int64_t count);
 
 /* ---- resident (device-side) interface: what bench.py times with inputs already in HBM -------- */
 /* H2D copy of one subproblem's inputs into slot `slot` (asynchronous on the plan's stream). */
@@ -169,6 +222,8 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *  11 number of CUDA-graph replays performed by bb200_solve
  *  12 tile variant of the wavefront kernel (1-based, as accepted by bb200_plan_tune)
  *  13 scatter warps per CTA of the wavefront kernel
+ *  14 device time [ms] of the last bb200_solve_batched call (first prep kernel to last D2H)
+ *  15 waves of that call            16 host waits (event synchronisations) of all batched calls so far
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);
 

@@ -35,8 +35,24 @@ SIGNATURES = {
     "bb200_select_and_backtrack": (ctypes.c_int, [c_plan_p, ctypes.c_int64, _F64P, _F64P, _I64P, _I64P]),
     "bb200_solve": (ctypes.c_int, [c_plan_p, _F64P, _F64P, ctypes.c_int64, _F64P, _F64P, _I64P, _I64P]),
     "bb200_solve_batched": (ctypes.c_int, [c_plan_p, ctypes.c_int64, _F64P, _F64P, ctypes.c_int32, _I64P,
-                                           _F64P, _F64P, _I64P, _I64P]),
+                                           _F64P, _F64P, _I64P, _I64P, _I32P]),
+    "bb200_solve_batched_shard": (ctypes.c_int, [c_plan_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _F64P, _F64P,
+                                                 ctypes.c_int32, _I64P, _F64P, _F64P, _I64P, _I64P, _I32P]),
     "bb200_best_candidate": (ctypes.c_int, [_F64P, _I64P, ctypes.c_int64, _F64P, _I64P]),
+    "bb200_nccl_version": (ctypes.c_int, []),
+    "bb200_multi_create": (ctypes.c_int, [_I32P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_int64, _I64P, _I32P, _I64P, _F64P, ctypes.c_double,
+                                          ctypes.c_int32, ctypes.c_uint32, ctypes.POINTER(c_plan_p)]),
+    "bb200_multi_destroy": (ctypes.c_int, [c_plan_p]),
+    "bb200_multi_solve_batched": (ctypes.c_int, [c_plan_p, ctypes.c_int64, _F64P, _F64P, ctypes.c_int32, _I64P, _F64P,
+                                                 _F64P, _I64P, _I64P, _I32P, _F64P, _I64P, _I32P, _F64P]),
+    "bb200_multi_stats": (ctypes.c_int, [c_plan_p, _F64P, ctypes.c_int32]),
+    "bb200_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "bb200_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                         ctypes.POINTER(c_plan_p)]),
+    "bb200_comm_destroy": (ctypes.c_int, [c_plan_p]),
+    "bb200_comm_best_candidate": (ctypes.c_int, [c_plan_p, ctypes.c_double, ctypes.c_int64, _F64P, _I64P, _I32P]),
+    "bb200_comm_broadcast": (ctypes.c_int, [c_plan_p, ctypes.c_int32, _F64P, ctypes.c_int64]),
     "bb200_upload": (ctypes.c_int, [c_plan_p, ctypes.c_int32, _F64P, _F64P]),
     "bb200_upload_device": (ctypes.c_int, [c_plan_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "bb200_bellman_resident": (ctypes.c_int, [c_plan_p, ctypes.c_int32, ctypes.c_int32]),

@@ -33,10 +33,15 @@ class TRMPlan:
 
     def __init__(self, nu, iterator, n, B, beta, p, dt, *, device=0, batch=1, flags=0, cost=None):
         self.lib = _lib.load()
-        self.nu = [list(map(int, v)) for v in nu]
+        for v in nu:
+            for x in v:
+                if float(x) != int(x):      # the reference's nu is Vector{Vector{Int64}} (multi-trust.jl:64)
+                    raise ValueError(f"control levels must be integers (the reference's nu is Int64); got {x!r}")
+        self.nu = [[int(x) for x in v] for v in nu]
         self.level_values, self.grid_offset, self.grid_dims = flatten(self.nu, iterator)
         self.n, self.M, self.K, self.B = int(n), len(self.nu), int(self.level_values.shape[0]), int(B)
         self.dt = float(dt)
+        self.beta, self.p = float(beta), p
         self.batch = int(batch)
         if cost is None:
             cost = jump_cost_table(beta, p, self.level_values)
@@ -78,8 +83,12 @@ class TRMPlan:
             _lib.f64p(u), ctypes.byref(ps), ctypes.byref(bs), ctypes.byref(ks)))
         return ps.value, bs.value, ks.value
 
-    def solve_batched(self, df_all, u_old_all, radii, want_u=True):
-        """S independent subproblems, each with len(radii) selections from its one table."""
+    def solve_batched(self, df_all, u_old_all, radii, want_u=True, *, first=0, stride=1, out=None, strict=True):
+        """S independent subproblems, each with len(radii) selections from its one table.
+
+        first/stride restrict the call to the shard {first, first+stride, ..} (indices stay global; the other rows of
+        the outputs are left untouched).  Returns (u_out, phi, b_star, k_star); with strict=False per-entry failures
+        (InexactError of one subproblem, a stale selection) do not raise and a fifth value, status (S, R), is returned."""
         df_all = np.ascontiguousarray(df_all, dtype=np.float64)
         u_old_all = np.ascontiguousarray(u_old_all, dtype=np.float64)
         S = df_all.shape[0]
@@ -87,14 +96,20 @@ class TRMPlan:
             raise ValueError("df_all/u_old_all must have shape (S, n, M)")
         radii = np.ascontiguousarray(radii, dtype=np.int64)
         R = radii.shape[0]
-        u_out = np.empty((S, R, self.n, self.M), dtype=np.float64) if want_u else None
-        phi = np.empty((S, R), dtype=np.float64)
-        bs = np.empty((S, R), dtype=np.int64)
-        ks = np.empty((S, R), dtype=np.int64)
-        _lib.check(self.lib.bb200_solve_batched(
-            self._h, S, _lib.f64p(df_all), _lib.f64p(u_old_all), R, _lib.i64p(radii),
-            _lib.f64p(u_out), _lib.f64p(phi), _lib.i64p(bs), _lib.i64p(ks)))
-        return u_out, phi, bs, ks
+        if out is None:
+            u_out = np.zeros((S, R, self.n, self.M), dtype=np.float64) if want_u else None
+            phi = np.full((S, R), np.nan, dtype=np.float64)
+            bs = np.full((S, R), -1, dtype=np.int64)
+            ks = np.full((S, R), -1, dtype=np.int64)
+            status = np.zeros((S, R), dtype=np.int32)
+        else:
+            u_out, phi, bs, ks, status = out
+        rc = self.lib.bb200_solve_batched_shard(
+            self._h, S, int(first), int(stride), _lib.f64p(df_all), _lib.f64p(u_old_all), R, _lib.i64p(radii),
+            _lib.f64p(u_out), _lib.f64p(phi), _lib.i64p(bs), _lib.i64p(ks), _lib.i32p(status))
+        if strict or rc not in (_lib.ERR_INEXACT, _lib.ERR_STALE):
+            _lib.check(rc)
+        return (u_out, phi, bs, ks) if strict else (u_out, phi, bs, ks, status)
 
     # ---- resident interface --------------------------------------------------------------------
     def upload(self, slot, df, u_old):
@@ -158,10 +173,11 @@ class TRMPlan:
         return v.value
 
     def stats(self):
-        out = np.zeros(14, dtype=np.float64)
-        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 14))
+        out = np.zeros(17, dtype=np.float64)
+        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 17))
         keys = ("dp_ms", "backtrack_ms", "launches", "path", "ctas", "rows_per_cta", "arg_bytes",
-                "device_bytes", "threads", "jsplit", "wave_ms", "graph_replays", "variant", "scatter_warps")
+                "device_bytes", "threads", "jsplit", "wave_ms", "graph_replays", "variant", "scatter_warps",
+                "batch_ms", "batch_waves", "batch_syncs")
         return dict(zip(keys, out.tolist()))
 
     def profile(self, enable=True, fetch=False, max_ctas=148):
@@ -186,36 +202,59 @@ def fp64_peak(device=0, mode=0, target_ms=300.0):
 _plans: dict = {}
 
 
-def _plan_for(U, Phi, builder):
+class _Entry:
+    """Plan + what it was built for + the trajectory the last bellman_TRM already produced."""
+    __slots__ = ("plan", "sig", "u_cache", "cache_ok")
+
+    def __init__(self, plan, sig):
+        self.plan, self.sig = plan, sig
+        self.u_cache = np.empty((plan.n, plan.M), dtype=np.float64)
+        self.cache_ok = False
+
+
+def _signature(n, M, B, beta, p, dt, nu, it):
+    """Everything that is baked into a plan at creation.  The reference's bellman_TRM! is stateless, so a caller may
+    reuse U/Phi with another beta, p, dt, nu or iterator (beta-continuation, parameter sweeps): the plan is then
+    rebuilt instead of silently answering for the old parameters."""
+    return (int(n), int(M), int(B), float(beta), (type(p).__name__, float(p)), float(dt),
+            tuple(tuple(int(x) for x in v) for v in nu), tuple(tuple(int(x) for x in t) for t in it))
+
+
+def _entry_for(U, Phi):
     key = id(U) if U is not None else id(Phi)
-    ent = _plans.get(key)
-    if ent is None:
-        if builder is None:
-            raise _lib.BellmanB200Error(_lib.ERR_STATE, "eval_u_TRM called before bellman_TRM for these tables")
-        ent = builder()
-        _plans[key] = ent
-        anchor = U if U is not None else Phi
-        try:
-            weakref.finalize(anchor, _plans.pop, key, None)
-        except TypeError:
-            pass
-    return ent
+    return key, _plans.get(key)
 
 
 def bellman_TRM(df, u_old, B, beta, p, dt, nu, U, Phi, iterator, *, device=0, write_back=False):
     """Drop-in for bellman_TRM! (HelpFunctions.jl:20).  The device keeps its own packed tables; the
-    caller's U/Phi are only filled when write_back=True (parity/debug)."""
+    caller's U/Phi are only filled when write_back=True (parity/debug).
+
+    The reference always calls eval_u_TRM!(.., B, ..) right after this (multi-trust.jl:112-113), so the whole inner
+    iteration -- H2D, DP, selection and backtrack for budget B, D2H -- goes out as ONE bb200_solve (a CUDA-graph
+    replay, one synchronisation); the trajectory is kept and handed out by the eval_u_TRM that follows."""
     u_old_a = np.asarray(u_old)
     n, M = u_old_a.shape
-    it = list(iterator)
-
-    def build():
-        return TRMPlan(nu, it, n, B, beta, p, dt, device=device)
-
-    plan = _plan_for(U, Phi, build)
-    if (plan.n, plan.M, plan.B) != (n, M, int(B)):
-        raise ValueError("tables were created for a different problem size")
-    plan.bellman(df, u_old)
+    it = [tuple(t) for t in iterator]
+    sig = _signature(n, M, B, beta, p, dt, nu, it)
+    key, ent = _entry_for(U, Phi)
+    if ent is None or ent.sig != sig:
+        if ent is not None:
+            ent.plan.close()
+        ent = _Entry(TRMPlan(nu, it, n, B, beta, p, dt, device=device), sig)
+        if key not in _plans:
+            anchor = U if U is not None else Phi
+            try:
+                weakref.finalize(anchor, _plans.pop, key, None)
+            except TypeError:
+                pass
+        _plans[key] = ent
+    plan = ent.plan
+    ent.cache_ok = False
+    try:
+        plan.solve(df, u_old, ent.u_cache, B)
+        ent.cache_ok = True
+    except _lib.StaleCellError:
+        pass    # no feasible trajectory for budget B: the reference fails in eval_u_TRM!, not here; the DP is resident
     if write_back:
         if Phi is not None:
             Phi[...] = plan.export_phi()
@@ -226,7 +265,15 @@ def bellman_TRM(df, u_old, B, beta, p, dt, nu, U, Phi, iterator, *, device=0, wr
 
 def eval_u_TRM(u, u_old, U, Phi, B, nu, *, info=None):
     """Drop-in for eval_u_TRM! (HelpFunctions.jl:98); B may be any budget <= the table's."""
-    plan = _plan_for(U, Phi, None)
+    _, ent = _entry_for(U, Phi)
+    if ent is None:
+        raise _lib.BellmanB200Error(_lib.ERR_STATE, "eval_u_TRM called before bellman_TRM for these tables")
+    plan = ent.plan
+    if int(B) == plan.B and ent.cache_ok and info is None:
+        if u.shape != ent.u_cache.shape:
+            raise ValueError("u must have shape (n, M)")
+        u[...] = ent.u_cache       # produced by the bb200_solve of the bellman_TRM just before
+        return None
     ps, bs, ks = plan.eval_u(u, B)
     if info is not None:
         info.update(phi_star=ps, b_star=bs, k_star=ks, g_star=int(plan.grid_offset[ks]) if ks >= 0 else -1)

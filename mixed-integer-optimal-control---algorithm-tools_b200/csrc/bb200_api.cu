@@ -53,8 +53,6 @@ struct SlotHost {
     bool has_dp = false;
 };
 
-constexpr int kMaxRadii = 16;
-
 }  // namespace
 
 struct bb200_plan {
@@ -80,6 +78,18 @@ struct bb200_plan {
     std::vector<SlotDev> slots_dev;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *d_rec_all = nullptr;  // [batch][kRecDoubles]: the slots' record blocks, contiguous (one D2H per wave)
+    // batched radius sweep (bb200_solve_batched): trial budgets, per-(slot, radius) trajectories, second stream,
+    // double-buffered pinned staging so that the H2D of wave w+1 and the D2H of wave w-1 overlap the DP of wave w
+    int *d_radii = nullptr;
+    double *d_usweep = nullptr;
+    size_t usweep_elems = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_prep = nullptr, ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_batch[2] = {nullptr, nullptr};
+    double *h_in[2] = {nullptr, nullptr}, *h_out[2] = {nullptr, nullptr}, *h_recs[2] = {nullptr, nullptr};
+    int *h_errs[2] = {nullptr, nullptr};
+    size_t h_in_elems = 0, h_out_elems = 0;
+    double last_batch_ms = 0., batch_syncs = 0., batch_waves = 0.;
     // pinned staging
     double *h_rec = nullptr;
     int *h_err = nullptr;
@@ -105,6 +115,12 @@ struct bb200_plan {
 };
 
 namespace {
+
+int decouple_env()
+{
+    static const int v = [] { const char *e = getenv("BELLMAN_B200_DECOUPLE"); return e ? atoi(e) : 0; }();
+    return v;
+}
 
 template <typename T>
 int dev_alloc(bb200_plan *p, T **ptr, size_t count)
@@ -156,10 +172,23 @@ void destroy_plan(bb200_plan *p)
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->own_stream) cudaStreamSynchronize(p->own_stream);
+    if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     for (auto &s : p->slots) {
-        cudaFree(s.df); cudaFree(s.u_old); cudaFree(s.u); cudaFree(s.phi); cudaFree(s.rec);
+        cudaFree(s.df); cudaFree(s.u_old); cudaFree(s.u); cudaFree(s.phi);
         cudaFree(s.arg); cudaFree(s.n_updates); cudaFree(s.ss_all); cudaFree(s.bt_all);
     }
+    cudaFree(p->d_rec_all); cudaFree(p->d_radii); cudaFree(p->d_usweep);
+    for (int k = 0; k < 2; ++k) {
+        if (p->h_in[k]) cudaFreeHost(p->h_in[k]);
+        if (p->h_out[k]) cudaFreeHost(p->h_out[k]);
+        if (p->h_recs[k]) cudaFreeHost(p->h_recs[k]);
+        if (p->h_errs[k]) cudaFreeHost(p->h_errs[k]);
+        if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
+        if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
+        if (p->ev_batch[k]) cudaEventDestroy(p->ev_batch[k]);
+    }
+    if (p->ev_prep) cudaEventDestroy(p->ev_prep);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     cudaFree(p->d_lvd); cudaFree(p->d_cost); cudaFree(p->d_halo); cudaFree(p->d_scalar);
     cudaFree(p->d_goff); cudaFree(p->d_flags); cudaFree(p->d_err); cudaFree(p->d_btmax);
     cudaFree(p->d_slots);
@@ -178,18 +207,20 @@ void destroy_plan(bb200_plan *p)
 }
 
 // Queue the DP for slots [slot0, slot0+count) on the plan's stream.
-int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false)
+int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false, cudaEvent_t after_prep = nullptr)
 {
     cudaStream_t st = p->stream;
     if (!capturing) CU(cudaEventRecord(p->ev[0], st));
     CU(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(int), st));
     CU(cudaMemsetAsync(p->d_btmax, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(p->d_rec_all + (size_t)slot0 * kRecDoubles, 0, (size_t)count * kRecDoubles * sizeof(double), st));
     for (int s = slot0; s < slot0 + count; ++s) {
         CU(cudaMemsetAsync(p->slots[s].n_updates, 0, sizeof(unsigned long long), st));
         launch_prep(p->tab, p->slots_dev[s], p->d_err, p->d_btmax, st);
         p->launches += 1;
         p->slots[s].has_dp = true;
     }
+    if (after_prep) CU(cudaEventRecord(after_prep, st));  // df / u_old of these slots may be overwritten from here on
     if (p->mini_ok) {
         if (!capturing) CU(cudaEventRecord(p->ev[4], st));
         CU(launch_mini(p->tab, p->d_slots + slot0, count, p->argw, st));
@@ -211,7 +242,7 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false)
             c.err = p->d_err;
             c.btmax = p->d_btmax;
             c.prof = p->prof_on ? p->d_prof : nullptr;
-            c.decouple = (p->prof_on && getenv("BELLMAN_B200_DECOUPLE")) ? atoi(getenv("BELLMAN_B200_DECOUPLE")) : 0;  // profiling experiment, never a result
+            c.decouple = p->prof_on ? decouple_env() : 0;  // profiling experiment (PROF instantiation only), never a result
             CU(launch_wavefront(p->tab, c, p->argw, st));
             done += chunk;
             if (done < count) p->launches += 1;
@@ -335,6 +366,16 @@ struct Guard {
 
 }  // namespace
 
+namespace bb200 {
+// the calling thread's last-error message, for the other host translation units (bb200_multi.cu)
+int set_error(int code, const char *msg)
+{
+    g_err = msg;
+    return code;
+}
+const char *get_error() { return g_err.c_str(); }
+}  // namespace bb200
+
 extern "C" {
 
 const char *bb200_last_error(void) { return g_err.c_str(); }
@@ -416,6 +457,8 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
     p->tab.n = (int)n; p->tab.M = M; p->tab.K = K; p->tab.Kp = p->Kp; p->tab.B1 = p->B1; p->tab.dt = dt;
     p->tab.lvd = p->d_lvd; p->tab.cost = p->d_cost; p->tab.goff = p->d_goff;
 
+    if ((rc = dev_alloc(p, &p->d_rec_all, (size_t)batch * kRecDoubles))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_radii, (size_t)kMaxRadii))) return bail(rc);
     p->slots.resize(batch);
     p->slots_dev.resize(batch);
     const size_t io = (size_t)p->nPad * M;
@@ -426,7 +469,7 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
         if ((rc = dev_alloc(p, &h.u_old, io))) return bail(rc);
         if ((rc = dev_alloc(p, &h.u, io))) return bail(rc);
         if ((rc = dev_alloc(p, &h.phi, (size_t)2 * p->B1 * p->Kp))) return bail(rc);
-        if ((rc = dev_alloc(p, &h.rec, (size_t)4 * kMaxRadii))) return bail(rc);
+        h.rec = p->d_rec_all + (size_t)s * kRecDoubles;
         if ((rc = dev_alloc(p, &h.n_updates, 1))) return bail(rc);
         if ((rc = dev_alloc(p, &h.ss_all, (size_t)n * p->Kp))) return bail(rc);
         if ((rc = dev_alloc(p, &h.bt_all, (size_t)n * p->Kp))) return bail(rc);
@@ -444,7 +487,8 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
     CUB(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
     p->stream = p->own_stream;
     for (auto &e : p->ev) CUB(cudaEventCreate(&e));
-    CUB(cudaMallocHost((void **)&p->h_rec, 4 * kMaxRadii * sizeof(double)));
+    CUB(cudaMallocHost((void **)&p->h_rec, kRecDoubles * sizeof(double)));
+    CUB(cudaMemset(p->d_rec_all, 0, (size_t)batch * kRecDoubles * sizeof(double)));
     CUB(cudaMallocHost((void **)&p->h_err, 4 * sizeof(int)));
 #undef CUB
     if ((rc = reconfigure(p))) return bail(rc);
@@ -630,51 +674,194 @@ int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t
     return download_locked(plan, 0, 0, u_out, phi_star, b_star, k_star);
 }
 
-int bb200_solve_batched(bb200_plan *plan, int64_t S, const double *df_all, const double *u_old_all,
-                        int32_t n_radii, const int64_t *B_new, double *u_out_all, double *phi_star,
-                        int64_t *b_star, int64_t *k_star)
+// ---- batched radius sweep as a pipeline -----------------------------------------------------------------------
+// Lazily creates what only the batched path needs: the copy stream, the events and the pinned staging buffers
+// (inputs of one wave: [batch][2][n*M]; outputs: [batch][n_radii][n*M] + the record blocks), two of each.
+static int ensure_batch_pipe(bb200_plan *p, int n_radii, bool want_u)
+{
+    const size_t io = (size_t)p->n * p->M;
+    if (!p->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&p->ev_prep, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaEventCreateWithFlags(&p->ev_in[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_out[k], cudaEventDisableTiming));
+            CU(cudaEventCreate(&p->ev_batch[k]));
+            CU(cudaMallocHost((void **)&p->h_recs[k], (size_t)p->batch * kRecDoubles * sizeof(double)));
+            CU(cudaMallocHost((void **)&p->h_errs[k], 4 * sizeof(int)));
+        }
+    }
+    const size_t in_need = (size_t)p->batch * 2 * io;
+    if (in_need > p->h_in_elems) {
+        for (int k = 0; k < 2; ++k) {
+            if (p->h_in[k]) cudaFreeHost(p->h_in[k]);
+            p->h_in[k] = nullptr;
+            CU(cudaMallocHost((void **)&p->h_in[k], in_need * sizeof(double)));
+        }
+        p->h_in_elems = in_need;
+    }
+    const size_t out_need = want_u ? (size_t)p->batch * n_radii * io : 0;
+    if (out_need > p->h_out_elems) {
+        for (int k = 0; k < 2; ++k) {
+            if (p->h_out[k]) cudaFreeHost(p->h_out[k]);
+            p->h_out[k] = nullptr;
+            CU(cudaMallocHost((void **)&p->h_out[k], out_need * sizeof(double)));
+        }
+        p->h_out_elems = out_need;
+    }
+    const size_t sweep_need = (size_t)p->batch * n_radii * io;
+    if (sweep_need > p->usweep_elems) {
+        CU(cudaStreamSynchronize(p->stream));
+        if (p->d_usweep) { cudaFree(p->d_usweep); p->dev_bytes -= p->usweep_elems * sizeof(double); }
+        p->d_usweep = nullptr;
+        p->usweep_elems = 0;
+        int rc = dev_alloc(p, &p->d_usweep, sweep_need);
+        if (rc) return rc;
+        p->usweep_elems = sweep_need;
+    }
+    return BB200_OK;
+}
+
+// The subproblems first, first + stride, ... < S of the caller's arrays, in waves of `batch` resident slots:
+//   copy stream:     H2D(w+1) as soon as the prep kernels of wave w have consumed df / u_old
+//   compute stream:  prep(w) -> DP(w) (one persistent launch for all slots of the wave) -> ONE selection and ONE
+//                    backtrack launch with a CTA per (slot, radius) -> D2H(w) into pinned staging
+//   host:            stages wave w+1 while wave w runs; one event wait per wave (for the outputs of wave w-1)
+int bb200_solve_batched_shard(bb200_plan *plan, int64_t S, int64_t first, int64_t stride, const double *df_all,
+                              const double *u_old_all, int32_t n_radii, const int64_t *B_new, double *u_out_all,
+                              double *phi_star, int64_t *b_star, int64_t *k_star, int32_t *status)
 {
     if (!plan) return fail(BB200_ERR_ARG, "plan is NULL");
     if (S < 1 || !df_all || !u_old_all) return fail(BB200_ERR_ARG, "bad batch arguments");
+    if (first < 0 || stride < 1) return fail(BB200_ERR_ARG, "bad shard (first=%lld, stride=%lld)", (long long)first, (long long)stride);
     if (n_radii < 1 || n_radii > kMaxRadii || !B_new) return fail(BB200_ERR_ARG, "n_radii=%d outside [1, %d]", n_radii, kMaxRadii);
+    for (int r = 0; r < n_radii; ++r)
+        if (B_new[r] < 0 || B_new[r] > plan->B) return fail(BB200_ERR_ARG, "B_new[%d]=%lld outside [0, %lld]", r, (long long)B_new[r], (long long)plan->B);
     Guard g(plan);
+    const int64_t mine = first < S ? (S - first + stride - 1) / stride : 0;  // subproblems of this shard
+    if (mine == 0) return BB200_OK;
+    const bool want_u = u_out_all != nullptr;
+    int rc = ensure_batch_pipe(plan, n_radii, want_u);
+    if (rc) return rc;
     const size_t io = (size_t)plan->n * plan->M;
+    const int batch = plan->batch;
+    const int64_t waves = (mine + batch - 1) / batch;
+    cudaStream_t st = plan->stream, cs = plan->copy_stream;
+    int radii[kMaxRadii];
+    for (int r = 0; r < n_radii; ++r) radii[r] = (int)B_new[r];
+    CU(cudaMemcpyAsync(plan->d_radii, radii, n_radii * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(plan->ev_batch[0], st));
+
+    auto sub = [&](int64_t w, int s) { return first + (w * batch + s) * stride; };  // global index of slot s in wave w
+    auto count = [&](int64_t w) { return (int)std::min<int64_t>(batch, mine - w * batch); };
+    auto stage_in = [&](int64_t w) -> int {  // host -> pinned -> device, on the copy stream
+        double *h = plan->h_in[w & 1];
+        const int cnt = count(w);
+        if (w >= 2) CU(cudaEventSynchronize(plan->ev_in[w & 1]));  // the H2D of wave w-2 has left this buffer (long ago)
+        for (int s = 0; s < cnt; ++s) {
+            std::memcpy(h + (size_t)(2 * s) * io, df_all + (size_t)sub(w, s) * io, io * sizeof(double));
+            std::memcpy(h + (size_t)(2 * s + 1) * io, u_old_all + (size_t)sub(w, s) * io, io * sizeof(double));
+        }
+        if (w > 0) CU(cudaStreamWaitEvent(cs, plan->ev_prep, 0));  // wave w-1's prep kernels have read their inputs
+        for (int s = 0; s < cnt; ++s) {
+            CU(cudaMemcpyAsync(plan->slots[s].df, h + (size_t)(2 * s) * io, io * sizeof(double), cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(plan->slots[s].u_old, h + (size_t)(2 * s + 1) * io, io * sizeof(double), cudaMemcpyHostToDevice, cs));
+        }
+        CU(cudaEventRecord(plan->ev_in[w & 1], cs));
+        return BB200_OK;
+    };
     int worst = BB200_OK;
     std::string worst_msg;
-    for (int64_t s0 = 0; s0 < S; s0 += plan->batch) {
-        const int cnt = (int)std::min<int64_t>(plan->batch, S - s0);
+    auto drain = [&](int64_t w) -> int {  // outputs of wave w: pinned -> the caller's arrays
+        CU(cudaEventSynchronize(plan->ev_out[w & 1]));
+        plan->batch_syncs += 1;
+        const int cnt = count(w);
+        const double *hr = plan->h_recs[w & 1];
+        const int *he = plan->h_errs[w & 1];
+        if (he[2]) return fail(BB200_ERR_CUDA, "wavefront kernel watchdog fired: a pipeline dependency was never satisfied");
         for (int s = 0; s < cnt; ++s) {
-            CU(cudaMemcpyAsync(plan->slots[s].df, df_all + (size_t)(s0 + s) * io, io * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
-            CU(cudaMemcpyAsync(plan->slots[s].u_old, u_old_all + (size_t)(s0 + s) * io, io * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
-        }
-        int rc = queue_dp(plan, 0, cnt);
-        if (rc) return rc;
-        for (int s = 0; s < cnt; ++s)
+            const int64_t gs = sub(w, s);
+            const bool inexact = hr[(size_t)s * kRecDoubles + 4 * kMaxRadii] != 0.;
             for (int r = 0; r < n_radii; ++r) {
-                rc = queue_backtrack(plan, s, B_new[r], r);
-                if (rc) return rc;
-                const size_t o = (size_t)(s0 + s) * n_radii + r;
-                rc = download_locked(plan, s, r, u_out_all ? u_out_all + o * io : nullptr,
-                                     phi_star ? phi_star + o : nullptr, b_star ? b_star + o : nullptr,
-                                     k_star ? k_star + o : nullptr);
-                if (rc == BB200_ERR_CUDA) return rc;
-                if (rc && !worst) { worst = rc; worst_msg = g_err; }
+                const double *rec = hr + (size_t)s * kRecDoubles + 4 * r;
+                const size_t o = (size_t)gs * n_radii + r;
+                const int code = inexact ? BB200_ERR_INEXACT : (rec[3] != 0. ? BB200_ERR_STALE : BB200_OK);
+                if (phi_star) phi_star[o] = rec[0];
+                if (b_star) b_star[o] = (int64_t)rec[1];
+                if (k_star) k_star[o] = (int64_t)rec[2];
+                if (status) status[o] = code;
+                if (want_u) std::memcpy(u_out_all + o * io, plan->h_out[w & 1] + ((size_t)s * n_radii + r) * io, io * sizeof(double));
+                if (code && (!worst || (code == BB200_ERR_INEXACT && worst == BB200_ERR_STALE))) {
+                    worst = code;
+                    char buf[256];
+                    snprintf(buf, sizeof buf, code == BB200_ERR_INEXACT
+                                 ? "subproblem %lld: InexactError: u_old is not integer valued / finite (HelpFunctions.jl:37,57)"
+                                 : "subproblem %lld, radius %d: selection/backtrack reached a cell the DP never wrote",
+                             (long long)gs, r);
+                    worst_msg = buf;
+                }
             }
+        }
+        return BB200_OK;
+    };
+
+    if ((rc = stage_in(0))) return rc;
+    for (int64_t w = 0; w < waves; ++w) {
+        const int cnt = count(w);
+        CU(cudaStreamWaitEvent(st, plan->ev_in[w & 1], 0));
+        rc = queue_dp(plan, 0, cnt, false, plan->ev_prep);
+        if (rc) return rc;
+        if (w + 1 < waves && (rc = stage_in(w + 1))) return rc;  // overlaps the DP of wave w
+        SweepDev sw{plan->d_slots, plan->d_radii, n_radii, plan->d_usweep, io};
+        CU(cudaMemsetAsync(plan->d_err + 1, 0, sizeof(int), st));
+        launch_select(plan->tab, plan->slots_dev[0], 0, nullptr, plan->d_err, st, &sw, cnt * n_radii);
+        launch_backtrack(plan->tab, plan->slots_dev[0], plan->argw, plan->d_err, st, &sw, cnt * n_radii);
+        plan->launches += 2;
+        CU(cudaGetLastError());
+        if (want_u)
+            CU(cudaMemcpyAsync(plan->h_out[w & 1], plan->d_usweep, (size_t)cnt * n_radii * io * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(plan->h_recs[w & 1], plan->d_rec_all, (size_t)cnt * kRecDoubles * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(plan->h_errs[w & 1], plan->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(plan->ev_out[w & 1], st));
+        if (w + 1 == waves) CU(cudaEventRecord(plan->ev_batch[1], st));
+        if (w > 0 && (rc = drain(w - 1))) return rc;
     }
+    if ((rc = drain(waves - 1))) return rc;
+    plan->dp_timed = false;
+    plan->batch_waves = (double)waves;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, plan->ev_batch[0], plan->ev_batch[1]) == cudaSuccess) plan->last_batch_ms = ms;
     if (worst) g_err = worst_msg;
     return worst;
 }
 
+int bb200_solve_batched(bb200_plan *plan, int64_t S, const double *df_all, const double *u_old_all,
+                        int32_t n_radii, const int64_t *B_new, double *u_out_all, double *phi_star,
+                        int64_t *b_star, int64_t *k_star, int32_t *status)
+{
+    return bb200_solve_batched_shard(plan, S, 0, 1, df_all, u_old_all, n_radii, B_new, u_out_all, phi_star, b_star,
+                                     k_star, status);
+}
+
+// Julia findmin order over (value, index) records, like the selection kernel (S8): NaN precedes every number,
+// -0.0 precedes +0.0, equal values go to the smaller index.
 int bb200_best_candidate(const double *values, const int64_t *indices, int64_t count, double *best_value,
                          int64_t *best_index)
 {
     if (!values || !indices || count < 1 || !best_value || !best_index) return fail(BB200_ERR_ARG, "bad arguments");
+    auto isless = [](double a, double b) {
+        if (a != a) return false;
+        if (b != b) return true;
+        if (a < b) return true;
+        if (a == b) return std::signbit(a) && !std::signbit(b);
+        return false;
+    };
+    auto isgreater = [&](double fm, double fx) { return (fm != fm || fx != fx) ? isless(fm, fx) : isless(fx, fm); };
     double bv = values[0];
     int64_t bi = indices[0];
     for (int64_t x = 1; x < count; ++x) {
         const double v = values[x];
-        const bool better = (v < bv) || (bv != bv && v == v) || (v == bv && indices[x] < bi) ||
-                            (v != v && bv != bv && indices[x] < bi);
+        const bool better = isgreater(bv, v) || (!isgreater(v, bv) && indices[x] < bi);
         if (better) { bv = v; bi = indices[x]; }
     }
     *best_value = bv;
@@ -825,13 +1012,14 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
 {
     if (!plan || !out) return fail(BB200_ERR_ARG, "bad arguments");
     Guard g(plan);
-    const double v[14] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+    const double v[17] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
                           plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
                           (double)plan->argw, (double)plan->dev_bytes,
                           plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.,
                           plan->last_wave_ms, plan->graph_replays,
-                          plan->wave_ok ? (double)(plan->cfg.variant + 1) : 0., plan->wave_ok ? (double)plan->cfg.NS : 0.};
-    for (int k = 0; k < count && k < 14; ++k) out[k] = v[k];
+                          plan->wave_ok ? (double)(plan->cfg.variant + 1) : 0., plan->wave_ok ? (double)plan->cfg.NS : 0.,
+                          plan->last_batch_ms, plan->batch_waves, plan->batch_syncs};
+    for (int k = 0; k < count && k < 17; ++k) out[k] = v[k];
     return BB200_OK;
 }
 

@@ -33,7 +33,21 @@ struct SlotDev {
     double *ss_all;       // [n][Kp] stage cost s_l(i) of stage i in row i-1 (filled by the prep kernel)
     int *bt_all;          // [n][Kp] budget use b~_l(i), clamped to B1 = unreachable; pad levels hold B1
     unsigned long long *n_updates;  // exact relaxation count of the last DP
-    double *rec;          // [4] phi_star, b_star, k_star, status of the last selection
+    double *rec;          // [kMaxRadii][4] phi_star, b_star, k_star, stale flag of selection r; then [4] slot status:
+                          // rec[4 * kMaxRadii] != 0: u_old of this slot is not integer valued (InexactError)
+};
+
+constexpr int kMaxRadii = 16;                    // selections per subproblem in one batched sweep
+constexpr int kRecDoubles = 4 * (kMaxRadii + 1);  // per-slot record block
+
+// Batched radius sweep (multi-trust.jl:109-110 for many subproblems at once): CTA x of the selection / backtrack
+// launch serves slot x / n_radii with radius x % n_radii and writes its trajectory to u_sweep[x].
+struct SweepDev {
+    const SlotDev *slots;  // nullptr: single-slot launch
+    const int *radii;      // [n_radii] trial budgets B'
+    int n_radii;
+    double *u_sweep;       // [slots * n_radii][n][M]
+    size_t u_stride;       // n * M
 };
 
 struct Tables {

@@ -9,8 +9,11 @@ void launch_prep(const Tables &t, const SlotDev &slot, int *err, int *btmax, cud
 int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream_t st);
 bool mini_applicable(const Tables &t, size_t smem_max);
 cudaError_t launch_mini(const Tables &t, const SlotDev *d_slots, int count, int argw, cudaStream_t st);
-void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bnew_ptr, int *err, cudaStream_t st);
-void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st);
+// sweep == nullptr: one CTA for `slot`; otherwise `ctas` = slots * radii CTAs, one per (slot, radius) of the sweep
+void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bnew_ptr, int *err, cudaStream_t st,
+                   const SweepDev *sweep = nullptr, int ctas = 1);
+void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st,
+                      const SweepDev *sweep = nullptr, int ctas = 1);
 void launch_pred_integral(const Tables &t, const SlotDev &slot, double *out, cudaStream_t st);
 void launch_tv(const Tables &t, const SlotDev &slot, int mode, double *out, cudaStream_t st);
 

@@ -52,7 +52,10 @@ __global__ void prep_kernel(Tables t, SlotDev slot, int *err, int *btmax)
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_upd) atomicAdd(slot.n_updates, s_upd);
-        if (s_bad) atomicOr(&err[0], 1);
+        if (s_bad) {
+            atomicOr(&err[0], 1);
+            slot.rec[4 * kMaxRadii] = 1.;  // per-slot flag: one bad subproblem must not condemn its whole batch
+        }
         atomicMax(btmax, s_max);
     }
 }
@@ -252,10 +255,22 @@ __device__ __forceinline__ bool cand_precedes(const Cand &x, const Cand &y)
     return x.pos < y.pos;
 }
 
-__global__ void select_kernel(Tables t, SlotDev slot, int Bnew_arg, const int *bnew_ptr, int *err)
+// slot / radius / output of this CTA in a batched sweep launch
+__device__ __forceinline__ void sweep_slot(const SweepDev &sw, SlotDev &slot, int &Bnew)
+{
+    if (!sw.slots) return;
+    const int s = blockIdx.x / sw.n_radii, r = blockIdx.x - s * sw.n_radii;
+    slot = sw.slots[s];
+    slot.rec += 4 * r;
+    slot.u = sw.u_sweep + (size_t)blockIdx.x * sw.u_stride;
+    Bnew = sw.radii[r];
+}
+
+__global__ void select_kernel(Tables t, SlotDev slot, int Bnew_arg, const int *bnew_ptr, int *err, SweepDev sw)
 {
     // the graph-replayed path passes the trial budget through device memory so that one captured graph serves every B'
     int Bnew = bnew_ptr ? *bnew_ptr : Bnew_arg;
+    sweep_slot(sw, slot, Bnew);
     if (Bnew < 0) Bnew = 0;
     if (Bnew > t.B1 - 1) Bnew = t.B1 - 1;
     __shared__ Cand s_c[32];
@@ -316,8 +331,9 @@ __global__ void select_kernel(Tables t, SlotDev slot, int Bnew_arg, const int *b
 // window is reloaded around the actual budget.
 // ------------------------------------------------------------------------------------------------
 template <typename ArgT>
-__global__ void __launch_bounds__(256, 1) backtrack_kernel(Tables t, SlotDev slot, int *err, int S, int W)
+__global__ void __launch_bounds__(256, 1) backtrack_kernel(Tables t, SlotDev slot, int *err, int S, int W, SweepDev sw)
 {
+    { int unused = 0; sweep_slot(sw, slot, unused); }
     extern __shared__ __align__(128) unsigned char smem_bt[];
     const int Kp = t.Kp;
     const uint32_t win_bytes = (uint32_t)(((size_t)S * W * Kp * sizeof(ArgT) + 127) / 128 * 128);
@@ -548,13 +564,19 @@ int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream
     return launches;
 }
 
-void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bnew_ptr, int *err, cudaStream_t st)
+void launch_select(const Tables &t, const SlotDev &slot, int Bnew, const int *bnew_ptr, int *err, cudaStream_t st,
+                   const SweepDev *sweep, int ctas)
 {
-    select_kernel<<<1, 1024, 0, st>>>(t, slot, Bnew, bnew_ptr, err);
+    const SweepDev none{nullptr, nullptr, 1, nullptr, 0};
+    select_kernel<<<sweep ? ctas : 1, 1024, 0, st>>>(t, slot, Bnew, bnew_ptr, err, sweep ? *sweep : none);
 }
 
-void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st)
+void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, cudaStream_t st, const SweepDev *sweep,
+                      int ctas)
 {
+    const SweepDev none{nullptr, nullptr, 1, nullptr, 0};
+    const SweepDev sw = sweep ? *sweep : none;
+    const int grid = sweep ? ctas : 1;
     // window rows W: at most 16 (a step that uses more budget than the window holds falls back to one HBM read);
     // stages per chunk S: at most 32, two buffers within ~200 KB of shared memory
     int W = t.B1 < 16 ? t.B1 : 16;
@@ -567,10 +589,10 @@ void launch_backtrack(const Tables &t, const SlotDev &slot, int argw, int *err, 
     const size_t smem = 2 * (win_bytes + (size_t)S * t.Kp * sizeof(int)) + (size_t)S * sizeof(int) + 128;
     if (argw == 1) {
         cudaFuncSetAttribute(backtrack_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        backtrack_kernel<uint8_t><<<1, 256, smem, st>>>(t, slot, err, (int)S, W);
+        backtrack_kernel<uint8_t><<<grid, 256, smem, st>>>(t, slot, err, (int)S, W, sw);
     } else {
         cudaFuncSetAttribute(backtrack_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        backtrack_kernel<uint16_t><<<1, 256, smem, st>>>(t, slot, err, (int)S, W);
+        backtrack_kernel<uint16_t><<<grid, 256, smem, st>>>(t, slot, err, (int)S, W, sw);
     }
 }
 

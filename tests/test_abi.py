@@ -56,7 +56,9 @@ def test_best_candidate_host_reduction(built):
     idx = np.array([10, 42, 5, 17, 1], dtype=np.int64)
     bv, bi = ctypes.c_double(), ctypes.c_int64()
     assert lib.bb200_best_candidate(built._lib.f64p(vals), built._lib.i64p(idx), 5, ctypes.byref(bv), ctypes.byref(bi)) == 0
-    assert (bv.value, bi.value) == (-1.5, 17)  # ties go to the smallest global index, NaN never wins
+    assert np.isnan(bv.value) and bi.value == 5  # Julia findmin order like the selection: NaN precedes every number
+    assert lib.bb200_best_candidate(built._lib.f64p(vals[[0, 1, 3, 4]].copy()), built._lib.i64p(idx[[0, 1, 3, 4]].copy()), 4, ctypes.byref(bv), ctypes.byref(bi)) == 0
+    assert (bv.value, bi.value) == (-1.5, 17)  # ties go to the smallest global index
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="box has a GPU")

@@ -378,3 +378,61 @@ def test_resident_interface_multiple_slots_one_launch(gpu_lib, oracle):
         oracle.eval_u_TRM(ur, inst.u_old, U, Phi, 100, inst.nu)
         np.testing.assert_array_equal(u, ur)
     plan.close()
+
+
+def test_drop_in_rebuilds_the_plan_when_parameters_change(gpu_lib, oracle):
+    """The reference's bellman_TRM! is stateless: calling it again on the SAME U/Phi with another beta, p, dt or
+    iterator must answer for the new parameters (the plan used to be keyed on (n, M, B) only)."""
+    m, o = gpu_lib, oracle
+    rng = np.random.default_rng(21)
+    nu = [[0, 1, 2], [0, 1]]
+    it = o.product_iterator(nu)
+    n, B = 12, 6
+    lv = o.level_values(nu, it)
+    u_old = lv[rng.integers(0, len(it), size=n)].astype(np.float64)
+    df = np.round(rng.standard_normal((n, 2)) * 4) / 4
+    U, Phi = o.alloc_tables(nu, n, B)
+    it_small = [t for t in it if t[0] <= 2]
+    u_old_small = np.minimum(u_old, [1.0, 1.0])
+    for beta, p, dt, iterator, uo in ((0.25, 1, 1.0, it, u_old), (0.75, 1, 1.0, it, u_old), (0.75, 2, 1.0, it, u_old),
+                                      (0.75, 2, 0.5, it, u_old), (0.75, float("inf"), 0.5, it, u_old),
+                                      (0.75, 1, 0.5, it_small, u_old_small)):
+        Ur, Phir = o.alloc_tables(nu, n, B)
+        m.bellman_TRM(df, uo, B, beta, p, dt, nu, U, Phi, iterator, write_back=True)
+        o.bellman_TRM(df, uo, B, beta, p, dt, nu, Ur, Phir, iterator)
+        np.testing.assert_array_equal(Phi, Phir)
+        for Bn in (B, B // 2):
+            u, ur = np.zeros((n, 2)), np.zeros((n, 2))
+            m.eval_u_TRM(u, uo, U, Phi, Bn, nu)
+            o.eval_u_TRM(ur, uo, Ur, Phir, Bn, nu)
+            np.testing.assert_array_equal(u, ur)
+
+
+def test_drop_in_sequence_is_one_graph_replay_per_inner_iteration(gpu_lib, oracle):
+    """multi-trust.jl:112-113 always calls eval_u_TRM!(.., B, ..) right after bellman_TRM!: the drop-in serves that
+    pair with ONE bb200_solve (graph replay); smaller radii afterwards go to bb200_select_and_backtrack."""
+    m, o = gpu_lib, oracle
+    wl = importlib.import_module(m.__name__ + ".workloads")
+    api = importlib.import_module(m.__name__ + ".api")
+    inst = wl.example_shaped("heat", n=96, seed=12, tie_heavy=True)
+    U, Phi = o.alloc_tables(inst.nu, inst.n, inst.B)
+    Ur, Phir = o.alloc_tables(inst.nu, inst.n, inst.B)
+    rng = np.random.default_rng(3)
+    for k in range(3):
+        df = np.round(rng.standard_normal(inst.df.shape) * 4) / 4
+        m.bellman_TRM(df, inst.u_old, inst.B, inst.beta, inst.p, inst.dt, inst.nu, U, Phi, inst.iterator)
+        o.bellman_TRM(df, inst.u_old, inst.B, inst.beta, inst.p, inst.dt, inst.nu, Ur, Phir, inst.iterator)
+        ent = api._plans[id(U)]
+        replays = ent.plan.stats()["graph_replays"]
+        assert replays == k + 1
+        for Bn in (inst.B, inst.B // 2, inst.B // 4):
+            u, ur = np.zeros_like(inst.u_old), np.zeros_like(inst.u_old)
+            m.eval_u_TRM(u, inst.u_old, U, Phi, Bn, inst.nu)
+            o.eval_u_TRM(ur, inst.u_old, Ur, Phir, Bn, inst.nu)
+            np.testing.assert_array_equal(u, ur)
+        assert ent.plan.stats()["graph_replays"] == replays       # the radii did not re-run the DP
+
+
+def test_non_integer_levels_are_rejected(gpu_lib):
+    with pytest.raises(ValueError):
+        gpu_lib.TRMPlan([[0, 0.5, 1]], [(1,), (2,), (3,)], 4, 2, 0.5, 1, 1.0)
