@@ -257,3 +257,118 @@ def TRM(obj, par, x0, bellman, eval_u, max_outer=None):
     h.J = J + beta * o.TV_p(u, p)
     h.u = u.copy()
     return h
+
+
+# --------------------------------------------------------------------------------------------------------
+# Multi-start TRM in lock-step: the executable mirror of julia/MultiStartTRM.jl
+# --------------------------------------------------------------------------------------------------------
+def radius_ladder(par, dt):
+    """The trial budgets one outer iteration can ask for, in the order the inner loop visits them:
+    k = 1: B = floor(D0/dt) (multi-trust.jl:69); after the (k-1)-th halving: floor((D0/2^(k-1))/dt) (:109).
+    Returns (distinct budgets in visiting order, index into them for k = 1..kmax)."""
+    radii, index = [], []
+    dk = par.delta0
+    for _ in range(int(par.kmax)):
+        b = int(math.floor(dk / dt))
+        if not radii or radii[-1] != b:
+            radii.append(b)
+        index.append(len(radii) - 1)
+        dk = dk / 2
+    return radii, index
+
+
+def oracle_solve_batched(nu, iterator, beta, p, dt, B):
+    """A solve_batched callable backed by the CPU oracle (what the device's bb200_solve_batched computes)."""
+    def solve(df_all, u_old_all, radii):
+        A, n, M = df_all.shape
+        u_all = np.zeros((A, len(radii), n, M))
+        status = np.zeros((A, len(radii)), dtype=np.int32)
+        for a in range(A):
+            U, Phi = o.alloc_tables(nu, n, B)
+            o.bellman_TRM(df_all[a], u_old_all[a], B, beta, p, dt, nu, U, Phi, iterator)
+            for r, Bn in enumerate(radii):
+                try:
+                    o.eval_u_TRM(u_all[a, r], u_old_all[a], U, Phi, Bn, nu)
+                except IndexError:
+                    status[a, r] = 4
+        return u_all, status
+    return solve
+
+
+def TRM_multistart(objs, par, x0s, solve_batched, max_outer=None, max_radii=16):
+    """S trust-region loops (multi-trust.jl:92-163) advanced in lock-step.
+
+    Per outer iteration the starts that are still running share ONE batched DP call: their gradients and current
+    controls go in, and because a sweep over trial radii costs no extra DP (the reference re-runs only eval_u_TRM!
+    after a rejected step, multi-trust.jl:109-110), the trajectories for the whole halving ladder come back at once.
+    Each start then walks its own inner loop (:105-159) over its precomputed trajectories.  Every DP result is what the
+    single-start loop would have computed, so the per-start histories equal S independent TRM runs.
+
+    solve_batched(df_all (A, n, M), u_old_all (A, n, M), radii) -> (u_all (A, R, n, M), status (A, R))
+    Returns a list of History, one per start."""
+    S = len(objs)
+    dt, nu = objs[0].tau, objs[0].V
+    beta, p = par.beta, par.p
+    radii, kidx = radius_ladder(par, dt)
+    hs = [History() for _ in range(S)]
+    us, u_olds, J_olds, Js = [], [], [], [math.inf] * S
+    for s, obj in enumerate(objs):
+        u = obj.x
+        u[:] = x0s[s]
+        us.append(u)
+        u_olds.append(u.copy())
+        J_olds.append(obj.eval_f())
+        hs[s].rows.append((0, 0, par.delta0, J_olds[s] + beta * o.TV_p(u, p), 0.0, 0.0, "Initial Value"))
+    stop = [False] * S
+    iter_ = 1
+    maxiter = par.maxiter if max_outer is None else min(par.maxiter, max_outer)
+    while not all(stop) and iter_ <= maxiter:
+        act = [s for s in range(S) if not stop[s]]
+        TV_olds = {s: o.TV_p(us[s], p) for s in act}
+        for s in act:
+            objs[s].eval_df()
+        df_all = np.stack([objs[s].df for s in act])
+        uo_all = np.stack([u_olds[s] for s in act])
+        u_all, status = solve_batched(df_all, uo_all, radii[:max_radii])   # the first max_radii rungs of the ladder
+        for a, s in enumerate(act):
+            obj, h = objs[s], hs[s]
+            h.dp_calls += 1
+            dk, k = par.delta0, 1
+            ared, pred = 0.0, 1.0
+            TV_old = TV_olds[s]
+            lo, u_row, st_row = 0, u_all[a], status[a]     # radii[lo : lo + max_radii] are at hand for this start
+            while ared < par.sigma * pred and k <= par.kmax:
+                r = kidx[k - 1]
+                if not (lo <= r < lo + max_radii):         # deeper than that (only when B >= 2^max_radii): one more DP
+                    lo = r
+                    u_more, st_more = solve_batched(df_all[a:a + 1], uo_all[a:a + 1], radii[lo:lo + max_radii])
+                    u_row, st_row = u_more[0], st_more[0]
+                if st_row[r - lo] != 0:
+                    raise IndexError("backtrack visited a cell the DP never wrote")
+                us[s][:] = u_row[r - lo]
+                h.backtracks += 1
+                int_val = o.pred_integral(obj.df, u_olds[s], us[s], dt)
+                TV_new = o.TV_p(us[s], p)
+                J_new = obj.eval_f()
+                pred = int_val + beta * (TV_old - TV_new)
+                ared = J_olds[s] - J_new + beta * (TV_old - TV_new)
+                if pred <= 0:
+                    Js[s] = J_olds[s]
+                    stop[s] = True
+                    h.rows.append((iter_, k, dk, Js[s] + beta * TV_old, pred, ared, "optimal solution found"))
+                    break
+                elif ared < par.sigma * pred:
+                    h.rows.append((iter_, k, dk, J_olds[s] + beta * TV_old, pred, ared, "bad step, halved"))
+                    dk = dk / 2
+                else:
+                    u_olds[s][:] = us[s]
+                    J_olds[s] = J_new
+                    TV_old = TV_new
+                    Js[s] = J_new
+                    h.rows.append((iter_, k, dk, Js[s] + beta * TV_new, pred, ared, "good step"))
+                k += 1
+        iter_ += 1
+    for s in range(S):
+        hs[s].J = Js[s] + beta * o.TV_p(us[s], p)
+        hs[s].u = us[s].copy()
+    return hs
