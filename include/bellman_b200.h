@@ -224,6 +224,9 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *  13 scatter warps per CTA of the wavefront kernel
  *  14 device time [ms] of the last bb200_solve_batched call (first prep kernel to last D2H)
  *  15 waves of that call            16 host waits (event synchronisations) of all batched calls so far
+ *  17 candidates the last DP really evaluated when it ran the pruned scan (else 0): the exhaustive count is
+ *     bb200_count_updates; the difference was skipped by the bound test, results are bit-identical
+ *  18 block size of the pruned scan of the current geometry (0: exhaustive scan)
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);
 
@@ -249,7 +252,8 @@ int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t vari
  *   0 1 if the shape runs on the wavefront kernel, else 0      1 tile variant (1-based)
  *   2 rows per thread tile in sub-slice A   3 in sub-slice B (0: one sub-slice)   4 levels per thread tile
  *   5 CTAs   6 source rows per CTA   7 j-split   8 successors per j-group   9 rows of the padded jump-cost table
- *  10 scatter warps   11 threads per CTA   12 dynamic shared memory per CTA [bytes] */
+ *  10 scatter warps   11 threads per CTA   12 dynamic shared memory per CTA [bytes]
+ *  13 block size of the pruned scan (0: exhaustive scan) */
 int bb200_wave_geometry(int64_t n, int32_t M, int32_t K, int64_t B, int32_t num_sms, int64_t smem_max, int32_t ctas,
                         int32_t jsplit, int32_t variant, int64_t *out, int32_t count);
 

@@ -6,10 +6,10 @@ package does not need a GPU; calling into it does -- there is no CPU fallback.
 """
 from . import _lib
 from ._lib import BellmanB200Error, InexactError, StaleCellError
-from .api import TRMPlan, bellman_TRM, eval_u_TRM, fp64_peak
+from .api import Comm, MultiPlan, TRMPlan, bellman_TRM, eval_u_TRM, fp64_peak, nccl_version
 from .iterators import bounded_sum_iterator, flatten, jump_cost_table, product_iterator
 
-__all__ = ["TRMPlan", "bellman_TRM", "eval_u_TRM", "product_iterator", "bounded_sum_iterator", "flatten",
+__all__ = ["TRMPlan", "MultiPlan", "Comm", "nccl_version", "bellman_TRM", "eval_u_TRM", "product_iterator", "bounded_sum_iterator", "flatten",
            "jump_cost_table", "fp64_peak", "BellmanB200Error", "InexactError", "StaleCellError", "device_count"]
 
 

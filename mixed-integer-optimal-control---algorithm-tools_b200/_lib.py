@@ -88,6 +88,25 @@ class StaleCellError(BellmanB200Error, IndexError):
 _lib = None
 
 
+def _prefer_bundled_nccl():
+    """bb200_multi.cu binds NCCL at run time (dlopen).  In a Python process that also imports torch, both must end up
+    on the SAME NCCL: the dynamic loader reuses an already loaded libnccl.so.2 by SONAME, and torch's CUDA library needs
+    the (newer) NCCL it ships with.  So, unless the user chose one, point the library at the pip-bundled NCCL when it
+    exists; without torch (Julia, plain C) the system libnccl.so.2 is used."""
+    if os.environ.get("BELLMAN_B200_NCCL"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["BELLMAN_B200_NCCL"] = cand
+                return
+    except (ImportError, ValueError, AttributeError):
+        pass
+
+
 def load():
     """Load the shared library; raises if it has not been built (no fallback)."""
     global _lib
@@ -96,6 +115,7 @@ def load():
             raise ImportError(
                 f"{LIB_PATH} is missing: build the CUDA extension first "
                 "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        _prefer_bundled_nccl()
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)

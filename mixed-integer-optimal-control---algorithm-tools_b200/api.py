@@ -173,11 +173,11 @@ class TRMPlan:
         return v.value
 
     def stats(self):
-        out = np.zeros(17, dtype=np.float64)
-        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 17))
+        out = np.zeros(19, dtype=np.float64)
+        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 19))
         keys = ("dp_ms", "backtrack_ms", "launches", "path", "ctas", "rows_per_cta", "arg_bytes",
                 "device_bytes", "threads", "jsplit", "wave_ms", "graph_replays", "variant", "scatter_warps",
-                "batch_ms", "batch_waves", "batch_syncs")
+                "batch_ms", "batch_waves", "batch_syncs", "executed_updates", "prune_block")
         return dict(zip(keys, out.tolist()))
 
     def profile(self, enable=True, fetch=False, max_ctas=148):
@@ -278,3 +278,102 @@ def eval_u_TRM(u, u_old, U, Phi, B, nu, *, info=None):
     if info is not None:
         info.update(phi_star=ps, b_star=bs, k_star=ks, g_star=int(plan.grid_offset[ks]) if ks >= 0 else -1)
     return None
+
+
+# ---- multi-GPU behind the C ABI ---------------------------------------------------------
+def nccl_version():
+    """NCCL version the library bound at run time (0: NCCL not available)."""
+    return int(_lib.load().bb200_nccl_version())
+
+
+class MultiPlan:
+    """All GPUs of this process behind one handle: one plan and one host thread per device; subproblem s runs on
+    device s mod G; the best-candidate reduction is an ncclAllGather of 16-byte records inside the library."""
+
+    def __init__(self, devices, nu, iterator, n, B, beta, p, dt, *, batch_per_device=1, flags=0, cost=None):
+        self.lib = _lib.load()
+        self.nu = [[int(x) for x in v] for v in nu]
+        self.level_values, self.grid_offset, self.grid_dims = flatten(self.nu, iterator)
+        self.n, self.M, self.K, self.B = int(n), len(self.nu), int(self.level_values.shape[0]), int(B)
+        self.devices = np.ascontiguousarray(devices, dtype=np.int32)
+        if cost is None:
+            cost = jump_cost_table(beta, p, self.level_values)
+        self.cost = np.ascontiguousarray(cost, dtype=np.float64)
+        handle = _lib.c_plan_p()
+        _lib.check(self.lib.bb200_multi_create(
+            _lib.i32p(self.devices), int(self.devices.shape[0]), self.n, self.M, self.K, self.B,
+            _lib.i64p(self.grid_dims), _lib.i32p(np.ascontiguousarray(self.level_values)), _lib.i64p(self.grid_offset),
+            _lib.f64p(self.cost), float(dt), int(batch_per_device), int(flags), ctypes.byref(handle)))
+        self._h = handle
+        self._fin = weakref.finalize(self, self.lib.bb200_multi_destroy, handle)
+
+    def solve_batched(self, df_all, u_old_all, radii, want_u=True, want_best_u=True, strict=True):
+        """Returns dict(u, phi, b_star, k_star, status, best_value, best_subproblem, best_radius, u_best)."""
+        df_all = np.ascontiguousarray(df_all, dtype=np.float64)
+        u_old_all = np.ascontiguousarray(u_old_all, dtype=np.float64)
+        S = df_all.shape[0]
+        if df_all.shape != (S, self.n, self.M) or u_old_all.shape != df_all.shape:
+            raise ValueError("df_all/u_old_all must have shape (S, n, M)")
+        radii = np.ascontiguousarray(radii, dtype=np.int64)
+        R = radii.shape[0]
+        u_out = np.zeros((S, R, self.n, self.M), dtype=np.float64) if want_u else None
+        phi = np.full((S, R), np.nan)
+        bs = np.full((S, R), -1, dtype=np.int64)
+        ks = np.full((S, R), -1, dtype=np.int64)
+        status = np.zeros((S, R), dtype=np.int32)
+        u_best = np.zeros((self.n, self.M)) if want_best_u else None
+        bv, bsub, brad = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int32()
+        rc = self.lib.bb200_multi_solve_batched(
+            self._h, S, _lib.f64p(df_all), _lib.f64p(u_old_all), R, _lib.i64p(radii), _lib.f64p(u_out), _lib.f64p(phi),
+            _lib.i64p(bs), _lib.i64p(ks), _lib.i32p(status), ctypes.byref(bv), ctypes.byref(bsub), ctypes.byref(brad),
+            _lib.f64p(u_best))
+        if strict or rc not in (_lib.ERR_INEXACT, _lib.ERR_STALE):
+            _lib.check(rc)
+        return dict(u=u_out, phi=phi, b_star=bs, k_star=ks, status=status, best_value=bv.value,
+                    best_subproblem=bsub.value, best_radius=brad.value, u_best=u_best)
+
+    def stats(self):
+        out = np.zeros(2 + len(self.devices), dtype=np.float64)
+        _lib.check(self.lib.bb200_multi_stats(self._h, _lib.f64p(out), out.shape[0]))
+        return dict(devices=int(out[0]), wall_ms=out[1], device_ms=out[2:].tolist())
+
+    def close(self):
+        self._fin()
+
+
+class Comm:
+    """One rank of an NCCL communicator created through the C ABI (one process per GPU).  The 128-byte unique id is
+    drawn by rank 0 with `Comm.unique_id()` and shipped to the other ranks by the host program."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        _lib.check(_lib.load().bb200_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+        return buf.raw
+
+    def __init__(self, device, nranks, rank, uid: bytes):
+        self.lib = _lib.load()
+        if len(uid) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        buf = ctypes.create_string_buffer(uid, 128)
+        handle = _lib.c_plan_p()
+        _lib.check(self.lib.bb200_comm_create(int(device), int(nranks), int(rank), ctypes.cast(buf, ctypes.c_void_p),
+                                              ctypes.byref(handle)))
+        self._h = handle
+        self.rank, self.nranks = int(rank), int(nranks)
+        self._fin = weakref.finalize(self, self.lib.bb200_comm_destroy, handle)
+
+    def best_candidate(self, value, index):
+        bv, bi, own = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int32()
+        _lib.check(self.lib.bb200_comm_best_candidate(self._h, float(value), int(index), ctypes.byref(bv), ctypes.byref(bi),
+                                                      ctypes.byref(own)))
+        return bv.value, bi.value, own.value
+
+    def broadcast(self, root, array):
+        if array.dtype != np.float64 or not array.flags.c_contiguous:
+            raise ValueError("broadcast needs a C-contiguous float64 array")
+        _lib.check(self.lib.bb200_comm_broadcast(self._h, int(root), _lib.f64p(array), int(array.size)))
+        return array
+
+    def close(self):
+        self._fin()

@@ -71,6 +71,7 @@ struct bb200_plan {
     size_t halo_elems = 0;
     unsigned long long *d_flags = nullptr;
     int *d_err = nullptr, *d_btmax = nullptr;
+    unsigned long long *d_exec = nullptr;  // pruned scan: candidates really evaluated by the last DP
     long long *d_prof = nullptr;
     bool prof_on = false;
     SlotDev *d_slots = nullptr;
@@ -190,7 +191,7 @@ void destroy_plan(bb200_plan *p)
     if (p->ev_prep) cudaEventDestroy(p->ev_prep);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     cudaFree(p->d_lvd); cudaFree(p->d_cost); cudaFree(p->d_halo); cudaFree(p->d_scalar);
-    cudaFree(p->d_goff); cudaFree(p->d_flags); cudaFree(p->d_err); cudaFree(p->d_btmax);
+    cudaFree(p->d_goff); cudaFree(p->d_flags); cudaFree(p->d_err); cudaFree(p->d_btmax); cudaFree(p->d_exec);
     cudaFree(p->d_slots);
     cudaFree(p->d_prof);
     if (p->h_rec) cudaFreeHost(p->h_rec);
@@ -213,6 +214,7 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false, cudaEv
     if (!capturing) CU(cudaEventRecord(p->ev[0], st));
     CU(cudaMemsetAsync(p->d_err, 0, 4 * sizeof(int), st));
     CU(cudaMemsetAsync(p->d_btmax, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(p->d_exec, 0, sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(p->d_rec_all + (size_t)slot0 * kRecDoubles, 0, (size_t)count * kRecDoubles * sizeof(double), st));
     for (int s = slot0; s < slot0 + count; ++s) {
         CU(cudaMemsetAsync(p->slots[s].n_updates, 0, sizeof(unsigned long long), st));
@@ -242,6 +244,7 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false, cudaEv
             c.err = p->d_err;
             c.btmax = p->d_btmax;
             c.prof = p->prof_on ? p->d_prof : nullptr;
+            c.exec = p->d_exec;
             c.decouple = p->prof_on ? decouple_env() : 0;  // profiling experiment (PROF instantiation only), never a result
             CU(launch_wavefront(p->tab, c, p->argw, st));
             done += chunk;
@@ -439,6 +442,7 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
     if ((rc = dev_alloc(p, &p->d_goff, goff.size()))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_err, 4))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_btmax, 1))) return bail(rc);
+    if ((rc = dev_alloc(p, &p->d_exec, 1))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_scalar, 8))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_flags, (size_t)prop.multiProcessorCount * kFlagStride))) return bail(rc);
     if ((rc = dev_alloc(p, &p->d_slots, (size_t)batch))) return bail(rc);
@@ -533,9 +537,9 @@ int bb200_wave_geometry(int64_t n, int32_t M, int32_t K, int64_t B, int32_t num_
     t.n = (int)n; t.M = M; t.K = K; t.Kp = (K + 31) / 32 * 32; t.B1 = (int)B + 1; t.dt = 1.0;
     WaveCfg c{};
     const bool ok = wave_configure(t, K <= 255 ? 1 : 2, num_sms, (size_t)smem_max, ctas, jsplit, variant, c);
-    const int64_t v[13] = {ok ? 1 : 0, ok ? c.variant + 1 : 0, c.TB, c.TBB, c.TL, c.G, c.R, c.JS, c.jper, c.Kr, c.NS,
-                           c.threads, (int64_t)c.smem};
-    for (int k = 0; k < count && k < 13; ++k) out[k] = ok || k == 0 ? v[k] : 0;
+    const int64_t v[14] = {ok ? 1 : 0, ok ? c.variant + 1 : 0, c.TB, c.TBB, c.TL, c.G, c.R, c.JS, c.jper, c.Kr, c.NS,
+                           c.threads, (int64_t)c.smem, c.PR};
+    for (int k = 0; k < count && k < 14; ++k) out[k] = ok || k == 0 ? v[k] : 0;
     return BB200_OK;
 }
 
@@ -1012,14 +1016,20 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
 {
     if (!plan || !out) return fail(BB200_ERR_ARG, "bad arguments");
     Guard g(plan);
-    const double v[17] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+    unsigned long long exec = 0;
+    if (count > 17 && plan->cfg.PR > 0 && plan->wave_ok) {
+        CU(cudaStreamSynchronize(plan->stream));
+        CU(cudaMemcpy(&exec, plan->d_exec, sizeof exec, cudaMemcpyDeviceToHost));
+    }
+    const double v[19] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
                           plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
                           (double)plan->argw, (double)plan->dev_bytes,
                           plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.,
                           plan->last_wave_ms, plan->graph_replays,
                           plan->wave_ok ? (double)(plan->cfg.variant + 1) : 0., plan->wave_ok ? (double)plan->cfg.NS : 0.,
-                          plan->last_batch_ms, plan->batch_waves, plan->batch_syncs};
-    for (int k = 0; k < count && k < 17; ++k) out[k] = v[k];
+                          plan->last_batch_ms, plan->batch_waves, plan->batch_syncs, (double)exec,
+                          plan->wave_ok ? (double)plan->cfg.PR : 0.};
+    for (int k = 0; k < count && k < 19; ++k) out[k] = v[k];
     return BB200_OK;
 }
 

@@ -34,6 +34,17 @@
 //     (own slice: shared memory; higher slice: global ring), the argmin to HBM once per cell as uint8 indexed
 //     by source row (coalesced rows).  Tiles with one j-group skip phase C: the thread scatters its finished
 //     cells from registers ("direct" mode).
+//   * Pruned scan (tiles with PR > 0; the default for wide level sets): the scan above is exhaustive like the
+//     reference's loops, but most candidates cannot win.  For a block of PR consecutive successors,
+//         LB = (s_l + min_{j in block} c_jl) + min_{j in block} P[b', j]
+//     is a lower bound of every candidate of the block in the SAME floating-point arithmetic (rounded addition is
+//     monotone in both operands), so if the running minimum is not greater than LB no candidate of the block can win
+//     the strict '>' (HelpFunctions.jl:73) and the block is skipped -- for the whole warp, by a vote, because only a
+//     warp-uniform skip saves issue slots.  Successors are still visited in ascending order, so the results are
+//     bit-identical (value, argmin and ties).  A lane is a level, a warp is 32 levels x a group of rows, the two row
+//     groups of a CTA run on different warps, the finished cells are scattered from registers (no phase C, no
+//     scatter warps).  The block minima of the jump costs are a per-launch table, those of the value rows are
+//     recomputed per stage by every warp for its own rows.
 //   * Code size is a first-order concern: five roles run different code on one SM and the code executed every
 //     stage has to stay below the 32 KB instruction-cache tier (it was 36 KB: 95 % hit rate, 6 % slower).  Hence
 //     one out-of-line wait loop, one phase-C unit in flight per warp, +Inf pad rows in the jump-cost table (every
@@ -132,9 +143,6 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
 #ifndef BB_UNROLL
 #define BB_UNROLL 4
 #endif
-#ifndef BB_CU
-#define BB_CU 1  /* unused since phase C walks its units one at a time */
-#endif
 // An empty volatile asm inside the update keeps the front end from turning `if (best > v) { best = v; arg = j; }`
 // into selects (DSETP + FSEL + FSEL + SEL: three instructions on the half-rate ALU pipe, which then binds the scan).
 // ptxas if-converts the short branch itself into three PREDICATED MOVES and spreads them over the ALU and the FMA
@@ -145,6 +153,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
 #define BB_KEEP_BRANCH
 #endif
 constexpr int kUnrollB = BB_UNROLL;  // successor pairs per trip of the phase-B loop
+constexpr bool kAutoPruned = false;  // may the geometry model pick pruned tiles by itself (wide level sets only)?
 constexpr int kNever = 0x7fffffff;  // "no bound": ticks are 32-bit, wave_configure refuses launches with >= 2^30 steps
 
 // shared-memory synchronisation words
@@ -168,6 +177,8 @@ struct Smem {
     double *pv;       // [JS*R*Kp] partial minima of the j-groups
     unsigned char *pa;  // ArgT[JS*R*Kp] partial argmins
     int *umap;        // [R*ceil(Kp/64)] phase-C work unit -> (row << 16) | first level
+    double *cmin;     // pruned scan: [Kr/PR][Kp] block minima of the jump costs, cmin[q][l] = min_{j in block q} c_jl
+    double *pmin;     // pruned scan: [compute warps][6 * Kr/PR] block minima of the warp's value rows ([Kr/PR][4] per row, [Kr/PR] merged, pad)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -175,16 +186,19 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int argw, unsigned char *base, Smem *s)
 {
     size_t off = 0;
-    size_t o[8];
-    const size_t sizes[8] = {SYNC_WORDS * sizeof(uint64_t),
+    size_t o[10];
+    const int nblk = c.PR ? c.Kr / c.PR : 0;
+    const size_t sizes[10] = {SYNC_WORDS * sizeof(uint64_t),
                              3 * (size_t)t.Kp * sizeof(double),
                              3 * (size_t)t.Kp * sizeof(int),
                              2 * (size_t)t.Kp * c.R * sizeof(double),
                              (size_t)c.Kr * t.Kp * sizeof(double),
                              (size_t)c.JS * c.R * t.Kp * sizeof(double),
                              (size_t)c.JS * c.R * t.Kp * (size_t)argw,
-                             (size_t)c.R * (t.Kp / 32) * sizeof(int)};
-    for (int k = 0; k < 8; ++k) {
+                             (size_t)c.R * (t.Kp / 32) * sizeof(int),
+                             (size_t)nblk * t.Kp * sizeof(double),
+                             (size_t)(c.tpg / 32) * nblk * 6 * sizeof(double)};
+    for (int k = 0; k < 10; ++k) {
         o[k] = off;
         off = align_up(off + sizes[k], 128);
     }
@@ -197,6 +211,8 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
         s->pv = reinterpret_cast<double *>(base + o[5]);
         s->pa = base + o[6];
         s->umap = reinterpret_cast<int *>(base + o[7]);
+        s->cmin = reinterpret_cast<double *>(base + o[8]);
+        s->pmin = reinterpret_cast<double *>(base + o[9]);
     }
     return off;
 }
@@ -279,6 +295,141 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
             }
         }
     }
+}
+
+// Pruned scan of one thread: TB rows x ONE level (lane = level), successors in blocks of BK (at most 32 blocks).
+//   Prow: the warp's value rows [r][Kp];  cs_l = cs + l: jump costs c[j][l] at stride Kp;  cm_l = cmin + l: their block
+//   minima at stride Kp;  pm / pmm: this warp's scratch for the block minima of its value rows;  s: stage cost of l.
+// Two passes, so that no decision depends on the order of the scan (no compare -> vote -> branch chain per block):
+//   1. block minima of the warp's rows, pm[q][r] = min_{j in block q} P[r][j] and pmm[q] = min_r pm[q][r] (NaN ignored: a
+//      NaN candidate never wins; pad columns may hold anything, they only lower a bound);
+//   2. an upper bound UB[r] of every cell's minimum: the smallest candidate of ONE seed block (the block with the
+//      smallest pmm -- any block gives a valid bound, this one a good one);
+//   3. LB[q][r] = (s + cmin[q][l]) + pm[q][r] is a lower bound of every candidate of block q in the same floating-point
+//      arithmetic (rounded addition is monotone in both operands).  If LB > UB for every cell of the warp, no candidate
+//      of the block can be a minimum or tie with one, so the block is dropped; first with a cheap test merged over the
+//      warp's rows ((s + cmin) + pmm against max_r UB), then exactly on the blocks that survive it.  The masks are
+//      OR-reduced over the warp: only a warp-uniform skip saves issue slots;
+//   4. the surviving blocks are scanned in ascending order with the reference's strict '>' from +Inf: the same minimum,
+//      the same (earliest) argmin, bit for bit.
+template <int TB, int BK, typename ArgT, bool PROF>
+__device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
+                                            const double *__restrict__ cm_l, double *__restrict__ pm,
+                                            double *__restrict__ pmm, double s, int nblk, int Kp, bool live, int lane,
+                                            double (&best)[TB][1], int (&arg)[TB][1], unsigned int &executed,
+                                            long long (&ph)[4])
+{
+    long long tq = 0;
+    if constexpr (PROF) tq = clock64();
+#define PH_LAP(k) do { if constexpr (PROF) { const long long tn = clock64(); ph[k] += tn - tq; tq = tn; } } while (0)
+    static_assert(TB <= 4 && BK % 2 == 0, "block minima are stored four rows wide; successors are taken in pairs");
+    constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
+    const double inf = d_inf();
+    // ---- 1. block minima (lane = block) and the seed block ---------------------------------------------------
+    double myv = inf;
+    int myq = lane;
+    if (lane < nblk) {
+        double mall = inf;
+#pragma unroll
+        for (int r = 0; r < TB; ++r) {
+            double m = inf;
+#pragma unroll
+            for (int jj = 0; jj < BK; jj += 2) {
+                const double2 w = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK + jj);
+                m = fmin(m, fmin(w.x, w.y));
+            }
+            pm[4 * lane + r] = m;
+            mall = fmin(mall, m);
+        }
+        pmm[lane] = mall;
+        myv = mall;
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, myv, w);
+        const int oq = __shfl_xor_sync(0xffffffffu, myq, w);
+        if (ov < myv || (ov == myv && oq < myq)) { myv = ov; myq = oq; }
+    }
+    const int qs = min(myq, nblk - 1);  // warp-uniform
+    __syncwarp();
+    PH_LAP(0);
+    // ---- 2. upper bounds from the seed block (values only) ---------------------------------------------------
+    double ub[TB];
+#pragma unroll
+    for (int r = 0; r < TB; ++r) ub[r] = inf;
+#pragma unroll
+    for (int jj = 0; jj < BK; jj += 2) {
+        const int j = qs * BK + jj;
+        const double a0 = __dadd_rn(s, cs_l[(size_t)j * Kp]);
+        const double a1 = __dadd_rn(s, cs_l[(size_t)(j + 1) * Kp]);
+#pragma unroll
+        for (int r = 0; r < TB; ++r) {
+            const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + j);
+            const double v0 = __dadd_rn(a0, x.x), v1 = __dadd_rn(a1, x.y);
+            if (ub[r] > v0) ub[r] = v0;
+            if (ub[r] > v1) ub[r] = v1;
+        }
+    }
+    double ubmax = -inf;
+#pragma unroll
+    for (int r = 0; r < TB; ++r) {
+        if (!live) ub[r] = -inf;  // idle lanes (pad levels) never ask for a block
+        if (ub[r] > ubmax) ubmax = ub[r];
+    }
+    PH_LAP(1);
+    // ---- 3. which blocks can hold a minimum of some cell of this warp? --------------------------------------
+    unsigned int mneed = 0;
+#pragma unroll 4
+    for (int q = 0; q < nblk; ++q) {
+        const double lb = __dadd_rn(__dadd_rn(s, cm_l[(size_t)q * Kp]), pmm[q]);
+        mneed |= (lb > ubmax ? 0u : 1u) << q;
+    }
+    unsigned int pneed = 0;
+    for (unsigned int m = __reduce_or_sync(0xffffffffu, mneed); m; m &= m - 1) {
+        const int q = __ffs(m) - 1;
+        const double amin = __dadd_rn(s, cm_l[(size_t)q * Kp]);
+        const double2 x = *reinterpret_cast<const double2 *>(pm + 4 * q);
+        const double2 y = *reinterpret_cast<const double2 *>(pm + 4 * q + 2);
+        const double pmq[4] = {x.x, x.y, y.x, y.y};
+        bool nd = false;
+#pragma unroll
+        for (int r = 0; r < TB; ++r) nd = nd || !(__dadd_rn(amin, pmq[r]) > ub[r]);
+        pneed |= (nd ? 1u : 0u) << q;
+    }
+    // ---- 4. exhaustive scan of the surviving blocks, ascending, strict '>' -----------------------------------
+#pragma unroll
+    for (int r = 0; r < TB; ++r) { best[r][0] = inf; arg[r][0] = MARKI; }
+    unsigned int mfinal = __reduce_or_sync(0xffffffffu, pneed);
+    PH_LAP(2);
+    for (unsigned int m = mfinal; m; m &= m - 1) {
+        const int j0 = (__ffs(m) - 1) * BK;
+        executed += 1;
+#pragma unroll
+        for (int jj = 0; jj < BK; jj += 2) {
+            const int j = j0 + jj;
+            double p0[TB], p1[TB];
+#pragma unroll
+            for (int r = 0; r < TB; ++r) {
+                const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + j);
+                p0[r] = x.x;
+                p1[r] = x.y;
+            }
+            const double a0 = __dadd_rn(s, cs_l[(size_t)j * Kp]);        // HelpFunctions.jl:67
+            const double a1 = __dadd_rn(s, cs_l[(size_t)(j + 1) * Kp]);
+#pragma unroll
+            for (int r = 0; r < TB; ++r) {
+                const double v = __dadd_rn(a0, p0[r]);                                 // :71
+                if (best[r][0] > v) { BB_KEEP_BRANCH; best[r][0] = v; arg[r][0] = j; }  // :73-76
+            }
+#pragma unroll
+            for (int r = 0; r < TB; ++r) {
+                const double v = __dadd_rn(a1, p1[r]);
+                if (best[r][0] > v) { BB_KEEP_BRANCH; best[r][0] = v; arg[r][0] = j + 1; }
+            }
+        }
+    }
+    PH_LAP(3);
+#undef PH_LAP
 }
 
 // scan + partial (min, argmin) of this thread's j-group into shared memory for phase C
@@ -598,7 +749,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
                 scanned_phase ^= 1u << v;
                 PROF_LAP(0);
                 const int ub = v == 0 ? 0 : c.RA * ublocks, ue = v == 0 ? c.RA * ublocks : R * ublocks;
-                if (c.decouple < 2) fin.rows(fa, ub, ue);
+                if (!PROF || c.decouple < 2) fin.rows(fa, ub, ue);
                 finished(v);
                 PROF_LAP(2);
             }
@@ -624,6 +775,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
 // A bounded watchdog turns a lost dependency into an error code instead of a hung GPU.
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 
+template <bool PROF>
 __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane)
 {
     const int g = blockIdx.x;
@@ -648,10 +800,12 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         ring_val = kNever;
         if (lane == 0) sts_release_u32(&sm.mbar[RING_OK], (unsigned int)ring_val);
     }
-    if (c.decouple) {  // timing experiment only (results are wrong): ignore the neighbours
-        pred_seen = kNever;
-        ring_val = kNever;
-        if (lane == 0) sts_release_u32(&sm.mbar[RING_OK], (unsigned int)ring_val);
+    if constexpr (PROF) {
+        if (c.decouple) {  // timing experiment of the profiling build only (results are wrong): ignore the neighbours
+            pred_seen = kNever;
+            ring_val = kNever;
+            if (lane == 0) sts_release_u32(&sm.mbar[RING_OK], (unsigned int)ring_val);
+        }
     }
     unsigned int idle = 0;
     long long pc[6] = {0, 0, 0, 0, 0, 0};  // profile: loop trips, idle trips, pred polls, succ polls, SM id, cost rows loaded
@@ -776,7 +930,7 @@ __device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c
 
 // MAXT is a multiple of 128: the register file is split evenly over the four schedulers, so the per-thread
 // budget is set by the scheduler that hosts the most warps.
-template <int TBA, int TBB, int TL, typename ArgT, int MAXT, bool PROF>
+template <int TBA, int TBB, int TL, typename ArgT, int MAXT, bool PROF, int PR>
 __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -787,7 +941,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     const int NC = c.JS * c.tpg;  // compute threads, then: comm warp, publisher warp, NS scatter warps
     const int g = blockIdx.x;
     const int K = t.K, Kp = t.Kp, R = c.R, n = t.n;
-    constexpr int NV = TBB > 0 ? 2 : 1;
+    constexpr int NV = (TBB > 0 && PR == 0) ? 2 : 1;  // the pruned scan runs its two row groups side by side: one hand-over
     const double inf = d_inf();
 
     // one-time: jump costs into shared memory, value rows to +Inf, barriers and counters
@@ -809,6 +963,17 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if constexpr (PR > 0) {  // block minima of the jump costs (pad rows are +Inf and never lower a minimum)
+        const int nblk = c.Kr / PR;
+        for (int x = tid; x < nblk * Kp; x += blockDim.x) {
+            const int q = x / Kp, l = x - q * Kp;
+            double m = inf;
+#pragma unroll
+            for (int jj = 0; jj < PR; ++jj) m = fmin(m, sm.cs[(size_t)(q * PR + jj) * Kp + l]);
+            sm.cmin[x] = m;
+        }
+        __syncthreads();
+    }
 
     if (tid >= NC + 64) {
         scatter_warp<ArgT, PROF>(t, c, sm, (tid - NC - 64) >> 5, tid & 31);
@@ -819,15 +984,21 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         return;
     }
     if (tid >= NC) {
-        comm_warp(t, c, sm, tid - NC);
+        comm_warp<PROF>(t, c, sm, tid - NC);
         return;
     }
 
     // ========================================= COMPUTE warps ============================================
-    const int jg = tid / c.tpg, tig = tid % c.tpg;
-    const bool active = tig < c.RG * c.nLG;
-    const int rg = active ? tig / c.nLG : 0;
-    const int lg = active ? tig % c.nLG : 0;
+    // Pruned scan (PR > 0): a lane is a level, a warp is a block of 32 levels x one of the two row groups (rows
+    // [0, TBA) and [TBA, TBA + TBB)); the warps of row group 1 follow those of group 0, so that every scheduler hosts
+    // one warp of each group.
+    const int nLB = Kp >> 5;
+    const int pr_grp = PR > 0 ? (tid >> 5) / nLB : 0;
+    const int pr_l = PR > 0 ? (((tid >> 5) % nLB) << 5) + (tid & 31) : 0;
+    const int jg = PR > 0 ? 0 : tid / c.tpg, tig = tid % c.tpg;
+    const bool active = PR > 0 ? pr_l < K : tig < c.RG * c.nLG;
+    const int rg = (active && PR == 0) ? tig / c.nLG : 0;
+    const int lg = PR > 0 ? min(pr_l, Kp - 1) : (active ? tig % c.nLG : 0);
     const int jb = jg * c.jper;
     const int je = min(c.Kr, jb + c.jper);  // rows K .. Kr-1 of the cost table are +Inf: (s + Inf) + P never wins
     const int lane = tid & 31;
@@ -851,11 +1022,13 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             if (v == NV - 1) reds_release_inc(&sm.mbar[CNT_SCANNED]);
         }
     };
-    const int rowA = rg * TBA, rowB = c.RA + rg * TBB;
+    const int rowA = PR > 0 ? 0 : rg * TBA, rowB = PR > 0 ? TBA : c.RA + rg * TBB;
+    unsigned int executed = 0;  // pruned scan: blocks this warp really scanned
+    long long ph[4] = {0, 0, 0, 0};  // profile of the pruned scan: block minima + seed, upper bounds, masks, scan
     ArgT *pa = reinterpret_cast<ArgT *>(sm.pa);
 
     // tiles without a second sub-slice have no scatter warps: the compute warps finish their own stage
-    const bool self_finish = (TBB == 0) && (c.NS == 0);  // two sub-slices always have scatter warps
+    const bool self_finish = (TBB == 0 || PR > 0) && (c.NS == 0);  // two sub-slices one after the other always have scatter warps
     const bool direct = self_finish && c.JS == 1;         // final values stay in registers until they are scattered
     const int cwarp = tid >> 5;
     Finisher<ArgT, PROF> fin(t, c, sm, cwarp, NC >> 5, lane);
@@ -884,7 +1057,36 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             // ---- phase B: register-tiled min-plus scan over this group's successors, sub-slice A then B ------
             wait_finished(0);  // rows of A for stage i are complete (finish(A, i+1) or the terminal stage)
             PROF_LAP(0);
-            if (direct) {
+            if constexpr (PR > 0) {
+                // ---- pruned scan: block minima of my rows, branch-and-bound scan, scatter from registers ----------
+                static_assert(TL == 1, "pruned scan: a lane is a level");
+                double *pm = sm.pmin + (size_t)(tid >> 5) * (c.Kr / PR) * 6;  // [nblk][4] row minima, then [nblk] merged (16-byte aligned)
+                double *pmm = pm + (size_t)(c.Kr / PR) * 4;
+                const FinishArgs fa = fin.stage_args(sl, i, T);
+                if (pr_grp == 0) {
+                    double best[TBA][1];
+                    int arg[TBA][1];
+                    scan_pruned<TBA, PR, ArgT, PROF>(Pc, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, lane, best, arg, executed, ph);
+                    PROF_LAP(1);
+                    scanned(0);  // the comm warp may refill the rows this stage read
+                    fin.wait_inputs(i, T);
+                    PROF_LAP(2);
+                    if (active) scatter_tile<TBA, 1, ArgT>(fa, 0, lg, best, arg);
+                } else if constexpr (TBB > 0) {
+                    double best[TBB][1];
+                    int arg[TBB][1];
+                    scan_pruned<TBB, PR, ArgT, PROF>(Pc + (size_t)TBA * Kp, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, lane, best, arg, executed, ph);
+                    PROF_LAP(1);
+                    scanned(0);
+                    fin.wait_inputs(i, T);
+                    PROF_LAP(2);
+                    if (active) scatter_tile<TBB, 1, ArgT>(fa, TBA, lg, best, arg);
+                }
+                finished();
+                PROF_LAP(3);
+                pc[4] += 1;
+                continue;
+            } else if (direct) {
                 // ---- one j-group, no scatter warps: scan, then scatter the finished tile from registers ------------
                 double best[TBA][TL];
                 int arg[TBA][TL];
@@ -931,9 +1133,24 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         // drain: stage 1 (or the terminal stage when n == 1) is finished; keeps the barrier phases aligned
         for (int v = 0; v < NV; ++v) wait_finished(v);
     }
+    if constexpr (PR > 0) {  // candidates really evaluated: blocks x successors x rows x live lanes of this warp
+        if (c.exec && lane == 0) {
+            const int live = min(32, max(0, K - (((tid >> 5) % nLB) << 5)));
+            atomicAdd(c.exec, (unsigned long long)executed * (unsigned long long)(PR * (pr_grp == 0 ? TBA : TBB) * live));
+        }
+    }
     if (PROF && c.prof && tid == 0 && self_finish) {
         c.prof[(size_t)g * 16 + 14] = fin.pcc[0];
         c.prof[(size_t)g * 16 + 15] = fin.pcc[1];
+    }
+    if constexpr (PROF && PR > 0) {
+        if (c.prof && tid == 0) {  // the scatter warps' slots are free with pruned tiles: sub-phases of the scan (warp 0)
+            c.prof[(size_t)g * 16 + 5] = ph[0];
+            c.prof[(size_t)g * 16 + 6] = ph[1];
+            c.prof[(size_t)g * 16 + 7] = ph[2];
+            c.prof[(size_t)g * 16 + 14] = ph[3];
+            c.prof[(size_t)g * 16 + 15] = executed;
+        }
     }
     if (PROF && c.prof && tid == 0) {
         c.prof[(size_t)g * 16 + 0] = pc[0];
@@ -946,22 +1163,27 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-struct Variant { int TBA, TBB, TL; };
+struct Variant { int TBA, TBB, TL, PR; };
 // (rows of sub-slice A, rows of sub-slice B, levels) per thread tile.  TBB = 0: one sub-slice; phase C then runs
 // after the scan, either on the compute warps themselves (NS = 0) or on scatter warps.  Every variant is built for
 // CTAs of up to 512 threads (128 registers per thread, no spills).
+// The last column is PR, the block size of the pruned scan (0 = exhaustive scan).  Pruned tiles: lane = level, the two
+// row groups (TBA and TBB rows) run side by side on different warps, the compute warps finish their own stage; built for
+// CTAs of up to 384 threads (8 compute warps + comm + publisher, 168 registers per thread).
 #define BB200_VARIANTS(X)                                                                                      \
-    X(0, 7, 0, 2) X(1, 8, 0, 2) X(2, 6, 0, 2) X(3, 5, 0, 2) X(4, 4, 0, 2) X(5, 3, 0, 2) X(6, 2, 0, 2) X(7, 1, 0, 2) \
-    X(8, 8, 0, 1) X(9, 4, 0, 1) X(10, 2, 0, 1) X(11, 1, 0, 1)                                                    \
-    X(12, 4, 3, 2) X(13, 4, 4, 2) X(14, 3, 3, 2) X(15, 3, 2, 2) X(16, 2, 2, 2) X(17, 2, 1, 2) X(18, 1, 1, 2)     \
-    X(19, 4, 4, 1) X(20, 2, 2, 1) X(21, 1, 1, 1) X(22, 4, 3, 1) X(23, 3, 3, 1)
+    X(0, 7, 0, 2, 0) X(1, 8, 0, 2, 0) X(2, 6, 0, 2, 0) X(3, 5, 0, 2, 0) X(4, 4, 0, 2, 0) X(5, 3, 0, 2, 0) X(6, 2, 0, 2, 0) X(7, 1, 0, 2, 0) \
+    X(8, 8, 0, 1, 0) X(9, 4, 0, 1, 0) X(10, 2, 0, 1, 0) X(11, 1, 0, 1, 0)                                                    \
+    X(12, 4, 3, 2, 0) X(13, 4, 4, 2, 0) X(14, 3, 3, 2, 0) X(15, 3, 2, 2, 0) X(16, 2, 2, 2, 0) X(17, 2, 1, 2, 0) X(18, 1, 1, 2, 0)     \
+    X(19, 4, 4, 1, 0) X(20, 2, 2, 1, 0) X(21, 1, 1, 1, 0) X(22, 4, 3, 1, 0) X(23, 3, 3, 1, 0)                               \
+    X(24, 4, 3, 1, 4) X(25, 4, 3, 1, 8) X(26, 4, 4, 1, 4) X(27, 3, 3, 1, 4) X(28, 2, 2, 1, 4) X(29, 1, 1, 1, 4) X(30, 4, 0, 1, 4) X(31, 2, 0, 1, 4)
 static const Variant kVariants[] = {
-#define X(idx, a, b, l) {a, b, l},
+#define X(idx, a, b, l, pr) {a, b, l, pr},
     BB200_VARIANTS(X)
 #undef X
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kWaveThreads = kWaveThreadsSmall;
+constexpr int kWaveThreadsPruned = 384;  // pruned tiles: up to 10 compute warps + comm + publisher, 168 registers per thread
 
 static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int NS, WaveCfg &c)
 {
@@ -969,8 +1191,28 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int N
     c.TB = kVariants[v].TBA;
     c.TBB = kVariants[v].TBB;
     c.TL = kVariants[v].TL;
+    c.PR = kVariants[v].PR;
     const int tb = c.TB + c.TBB;
     const int rows_per_cta = (t.B1 + G - 1) / G;
+    if (c.PR > 0) {
+        // pruned scan: the CTA owns exactly the tile's rows (RG = 1), one lane per level, one warp per 32 levels and
+        // row group; the caller rejects the variant when the slices do not fit (rows_per_cta > tb)
+        c.RG = 1;
+        c.R = tb;
+        c.RA = c.TB;
+        c.RB = c.TBB;
+        c.G = (t.B1 + c.R - 1) / c.R;
+        c.nLG = t.K;
+        c.JS = 1;
+        c.jper = c.Kr = (t.K + c.PR - 1) / c.PR * c.PR;  // whole blocks; rows K .. Kr-1 of the cost table are +Inf
+        c.tpg = t.Kp * (c.TBB > 0 ? 2 : 1);              // 32 lanes per level block and row group
+        c.NS = 0;
+        c.EC = 2;
+        c.NF = c.tpg / 32;
+        c.threads = c.tpg + 64;
+        c.smem = carve(t, c, argw, nullptr, nullptr);
+        return;
+    }
     c.RG = (rows_per_cta + tb - 1) / tb;
     c.R = c.RG * tb;
     c.RA = c.RG * c.TB;
@@ -1009,17 +1251,26 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
     for (int v = 0; v < kNumVariants; ++v) {
         if (want_variant > 0 && v != want_variant - 1) continue;
         if (((t.K + kVariants[v].TL - 1) / kVariants[v].TL) * kVariants[v].TL > t.Kp) continue;
+        const int pr = kVariants[v].PR;
+        if (pr > 0) {
+            // the pruned scan pays when a stage has many successors to skip; narrow level sets keep the exhaustive tiles
+            if (want_variant == 0 && (!kAutoPruned || t.K < 64)) continue;
+            if ((t.K + pr - 1) / pr * pr > t.Kp || (t.K + pr - 1) / pr > 32) continue;  // whole blocks, one mask word
+        }
         for (int js = 1; js <= 16; ++js) {
             if (want_js > 0 && js != want_js) continue;
             if (js > t.K) break;
+            if (pr > 0 && js > 1) break;  // one thread scans all successors of its cells
             for (int nsi = 0; nsi < 7; ++nsi) {
                 const int ns = kNsChoices[nsi];
-                if (kVariants[v].TBB > 0 && ns == 0) continue;  // two sub-slices need scatter warps
+                if (kVariants[v].TBB > 0 && ns == 0 && pr == 0) continue;  // two sub-slices one after the other need scatter warps
+                if (pr > 0 && ns != 0) continue;                            // pruned scan: the compute warps finish the stage
                 if (want_ns > 0 && ns != want_ns % 10) continue;  // 100 * NS forces NS scatter warps, 1000: none
                 int gmax = want_ctas > 0 ? want_ctas : num_sms;
                 if (gmax > num_sms) gmax = num_sms;
                 WaveCfg c = cfg;
                 fill_geometry(t, argw, gmax, js, v, ns, c);
+                if (pr > 0 && (c.G > gmax || c.threads > kWaveThreadsPruned)) continue;  // the tile's rows x CTAs must cover the table
                 if (c.threads > kWaveThreads) continue;
                 if (c.smem > smem_max) continue;
                 if ((size_t)c.JS * c.R * t.Kp >= ((size_t)1 << 30) || (size_t)t.B1 * t.Kp >= ((size_t)1 << 31) ||
@@ -1052,7 +1303,14 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 };
                 const double sa = scan(c.TB), sb = scan(c.TBB);
                 double stage;
-                if (c.TBB > 0) {
+                if (pr > 0) {
+                    // per scheduler: the warps it hosts scan (TBA + TBB) rows x Kr successors between them; about half
+                    // of the blocks are skipped on the BASELINE shapes (the skip rate is data dependent: it is measured,
+                    // bb200_stats[17], not modelled); every block costs a bound check
+                    const int nlb = t.Kp / 32, per_sched = (nlb + 3) / 4;
+                    const double full = 7.0 * (c.TB + c.TBB) * c.Kr * per_sched;
+                    stage = 0.5 * full + (c.Kr / pr) * 40.0 * per_sched * (c.TBB > 0 ? 2 : 1) + 600.0;
+                } else if (c.TBB > 0) {
                     const double fa = finish(c.RA, true), fb = finish(c.RB, true);
                     // a shorter finish also shortens the lag a successor slice needs behind this one
                     stage = sa + sb + (fa > sb ? fa - sb : 0.) + (fb > sa ? fb - sa : 0.) + 0.15 * (fa + fb) + 800.0;
@@ -1074,13 +1332,14 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
     return found;
 }
 
-template <int TBA, int TBB, int TL>
+template <int TBA, int TBB, int TL, int PR>
 static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStream_t st)
 {
     void *args[] = {(void *)&t, (void *)&cfg};
+    constexpr int MAXT = PR > 0 ? kWaveThreadsPruned : kWaveThreads;
     // the cycle counters are a separate instantiation: their code would cost the production kernel ~1.5 %
-    const void *fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, kWaveThreads, true>
-                              : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, kWaveThreads, false>;
+    const void *fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR>
+                              : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     // cooperative launch: the CTAs wait on one another, so all of them must be co-resident
@@ -1091,7 +1350,7 @@ cudaError_t launch_wavefront(const Tables &t, const WaveCfg &cfg, int argw, cuda
 {
     if (argw != 1) return cudaErrorInvalidValue;
     switch (cfg.variant) {
-#define X(idx, a, b, l) case idx: return launch_variant<a, b, l>(t, cfg, st);
+#define X(idx, a, b, l, pr) case idx: return launch_variant<a, b, l, pr>(t, cfg, st);
         BB200_VARIANTS(X)
 #undef X
         default: return cudaErrorInvalidValue;

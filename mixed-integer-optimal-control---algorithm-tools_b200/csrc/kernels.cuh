@@ -28,6 +28,7 @@ struct WaveCfg {
     int RA, RB;   // rows of sub-slice A (lower) and B (upper): RG * TB, RG * TBB
     int nLG;      // level groups = ceil(K / TL)
     int JS;       // j-split: thread groups scanning disjoint successor ranges
+    int PR;       // pruned scan: successors per block of the branch-and-bound scan (0 = off), see kernel_wavefront.cu
     int jper;     // successors per group = ceil(K / JS), rounded up to even (to 8 when the pad rows fit)
     int Kr;       // rows of the jump-cost table in shared memory: K, or JS * jper with +Inf pad rows
     int tpg;      // threads per group (multiple of 32)
@@ -43,6 +44,7 @@ struct WaveCfg {
     int *err;                    // [4]: inexact, stale, watchdog, abort
     const int *btmax;
     long long *prof;             // optional [G][16] cycle counters (NULL = off)
+    unsigned long long *exec;    // pruned scan: number of candidates actually evaluated by this launch (all CTAs)
     int decouple;                // timing experiments only: CTAs ignore their neighbours (wrong results)
 };
 

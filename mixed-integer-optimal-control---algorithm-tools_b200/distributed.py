@@ -1,11 +1,16 @@
-"""Multi-GPU sharding of independent subproblems.
+"""Multi-GPU sharding of independent subproblems for the one-process-per-GPU launch (torchrun).
 
 One DP is sequential in time, so one subproblem lives on one GPU; the box is partitioned over INDEPENDENT
 subproblems (multi-start x0; a sweep over trial radii costs no extra DP, multi-trust.jl:109-110).  There is no
 data-path collective.  The only exchange is the final best-candidate reduction: every rank contributes one
-16-byte (value, global subproblem index) record, gathered with torch.distributed.all_gather (NCCL over
-NVLink on the GPU box, gloo in the CPU tests) and reduced locally with the deterministic lexicographic
-rule "smallest value, then smallest index" (NCCL has no MINLOC), so every rank agrees on the winner.
+16-byte (value, global subproblem index) record and all ranks reduce the gathered records with the deterministic
+rule of the selection (Julia findmin order, then smallest index; NCCL has no MINLOC).
+
+The collective itself lives behind the C ABI (bb200_comm_*: ncclAllGather / ncclBroadcast over NVLink, NCCL bound
+at run time); this module is the thin caller: torch.distributed is only the side channel that ships the 128-byte NCCL
+unique id from rank 0 to the other ranks.  Without GPUs (the gloo tests on CPU) the same records are gathered with
+torch.distributed.all_gather and reduced by the same C function.  A single process that owns several GPUs does not
+need this module at all: api.MultiPlan drives them with one call.
 """
 from __future__ import annotations
 
@@ -14,6 +19,8 @@ import ctypes
 import numpy as np
 
 from . import _lib
+
+_comm = None
 
 
 def shard(S: int, rank: int, world: int):
@@ -31,8 +38,34 @@ def local_best(values, global_indices):
     return bv.value, bi.value
 
 
+def init_comm(local_device: int, group=None):
+    """Creates this rank's NCCL communicator through the C ABI (call once per process after init_process_group with
+    the nccl backend).  Returns the api.Comm, or None when there is nothing to communicate with."""
+    global _comm
+    import torch.distributed as dist
+    from .api import Comm
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    _comm = Comm(local_device, world, rank, box[0])
+    return _comm
+
+
+def close_comm():
+    global _comm
+    if _comm is not None:
+        _comm.close()
+        _comm = None
+
+
 def best_candidate(value: float, global_index: int, device=None, group=None):
     """All ranks call this with their local best; returns the global (value, index) on every rank."""
+    if _comm is not None:
+        bv, bi, _ = _comm.best_candidate(value, global_index)
+        return bv, bi
     import torch
     import torch.distributed as dist
 
@@ -51,6 +84,9 @@ def best_candidate(value: float, global_index: int, device=None, group=None):
 
 def fetch_winner_control(u_local, owner_rank: int, n: int, M: int, device=None, group=None):
     """Broadcast the winning control trajectory (n*M*8 bytes) from the rank that owns it."""
+    if _comm is not None:
+        buf = np.ascontiguousarray(u_local, dtype=np.float64).copy() if _comm.rank == owner_rank else np.zeros((n, M))
+        return _comm.broadcast(owner_rank, buf)
     import torch
     import torch.distributed as dist
 

@@ -69,3 +69,21 @@ def test_no_cpu_fallback(built):
     with pytest.raises(built.BellmanB200Error):
         built.bellman_TRM(np.zeros((4, 1)), np.zeros((4, 1)), 2, 0.5, 1, 1.0, [[0, 1]], None, np.zeros((2, 2, 3)),
                           built.product_iterator([[0, 1]]))
+
+
+def test_nccl_is_bound_at_run_time(built):
+    """bb200_multi.cu dlopens NCCL: the library itself has no link-time dependency on it."""
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", built._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl" not in needed
+    v = built.nccl_version()
+    assert v == 0 or v >= 22000          # present in this image (2.27 system / 2.28 torch-bundled); 0 only where NCCL is absent
+
+
+def test_multi_and_comm_argument_validation(built):
+    lib = built._lib.load()
+    h = built._lib.c_plan_p()
+    assert lib.bb200_multi_create(None, 0, 4, 1, 2, 2, None, None, None, None, 1.0, 1, 0, ctypes.byref(h)) == built._lib.ERR_ARG
+    assert lib.bb200_comm_create(0, 2, 5, None, ctypes.byref(h)) == built._lib.ERR_ARG
+    assert lib.bb200_comm_best_candidate(None, 0.0, 0, None, None, None) == built._lib.ERR_ARG
+    assert lib.bb200_multi_destroy(None) == 0 and lib.bb200_comm_destroy(None) == 0

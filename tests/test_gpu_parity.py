@@ -135,7 +135,10 @@ def test_synthetic_config4_shape_vs_oracle(gpu_lib, oracle, tie):
                                   dict(variant=213, jsplit=3), dict(variant=413), dict(ctas=16, variant=214),
                                   dict(variant=115), dict(variant=316), dict(variant=617), dict(variant=218),
                                   dict(variant=119), dict(ctas=30, variant=220), dict(variant=321),
-                                  dict(variant=822, jsplit=2)])
+                                  dict(variant=822, jsplit=2),
+                                  # pruned (branch-and-bound) scan: 4+4 rows fit the 212 budget rows on 27 CTAs etc.
+                                  dict(variant=25), dict(variant=26), dict(variant=27), dict(variant=28),
+                                  dict(variant=29), dict(variant=30), dict(variant=31), dict(variant=32)])
 def test_wavefront_geometries(gpu_lib, oracle, tune):
     """Every tile variant / CTA count / j-split / scatter-warp count (variant + 100 * NS) of the pipelined kernel
     gives identical bits."""
@@ -148,7 +151,10 @@ def test_wavefront_geometries(gpu_lib, oracle, tune):
 @pytest.mark.parametrize("levels,M,B,tune", [(9, 2, 150, None), (9, 2, 150, dict(variant=413, jsplit=4)),   # K = 81 -> Kp = 96
                                            (33, 1, 97, None), (33, 1, 97, dict(variant=1)),                # K = 33 -> Kp = 64
                                            (7, 1, 40, dict(variant=215)), (10, 2, 333, None),              # K = 7, K = 100
-                                           (10, 2, 333, dict(ctas=148, variant=614, jsplit=2))])
+                                           (10, 2, 333, dict(ctas=148, variant=614, jsplit=2)),
+                                           (9, 2, 150, dict(variant=25)), (33, 1, 97, dict(variant=27)),   # pruned scan
+                                           (7, 1, 40, dict(variant=29)), (10, 2, 333, dict(variant=26)),
+                                           (5, 3, 999, dict(variant=25)), (5, 3, 999, dict(variant=26))])  # K = 125
 def test_partially_filled_level_blocks(gpu_lib, oracle, levels, M, B, tune):
     """Level counts that are not multiples of 32 / 64: padded lanes, a half-filled last work unit in phase C, odd
     successor ranges in phase B -- all bits must still match."""
@@ -436,3 +442,93 @@ def test_drop_in_sequence_is_one_graph_replay_per_inner_iteration(gpu_lib, oracl
 def test_non_integer_levels_are_rejected(gpu_lib):
     with pytest.raises(ValueError):
         gpu_lib.TRMPlan([[0, 0.5, 1]], [(1,), (2,), (3,)], 4, 2, 0.5, 1, 1.0)
+
+
+@pytest.mark.parametrize("kind", ["ties", "random", "flat", "far"])
+def test_pruned_scan_is_exact_and_reports_what_it_skipped(gpu_lib, oracle, kind):
+    """The branch-and-bound scan (tile 25: 4 + 3 rows, blocks of 4 successors) must give the exhaustive scan's bits on
+    inputs that stress the bound test: heavy ties, beta = 0 (every block has the same jump-cost minimum), huge jump costs
+    (almost everything skipped), and it reports how many candidates it really evaluated."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.synthetic(n=60, B=999, seed=5, tie_heavy=(kind == "ties"))
+    beta = {"ties": 0.25, "random": 0.5, "flat": 0.0, "far": 50.0}[kind]
+    df = inst.df if kind != "flat" else np.zeros_like(inst.df)
+    st = check_against_oracle(gpu_lib, oracle, inst.nu, inst.iterator, inst.n, inst.B, df, inst.u_old, beta, inst.p,
+                              inst.dt, 4, radii=[999, 500, 3, 0], tune=dict(variant=25))
+    assert st["prune_block"] == 4 and st["ctas"] == 143
+    plan = gpu_lib.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, beta, inst.p, inst.dt, flags=4)
+    plan.tune(variant=25)
+    plan.bellman(df, inst.u_old)
+    st = plan.stats()
+    assert 0 < st["executed_updates"] <= plan.count_updates() * 1.05   # padded successors are counted, skipped ones are not
+    if kind == "far":
+        assert st["executed_updates"] < 0.5 * plan.count_updates()
+    plan.close()
+
+
+def _multi_case(gpu_lib, S=9, n=80, B=99):
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    insts = [wl.synthetic(n=n, B=B, seed=20251018 + 2 * s, levels=3, M=3, tie_heavy=(s % 2 == 0)) for s in range(S)]
+    return insts, np.stack([i.df for i in insts]), np.stack([i.u_old for i in insts])
+
+
+def test_batched_pipeline_reports_per_entry_status_and_one_wait_per_wave(gpu_lib, oracle):
+    """bb200_solve_batched: waves of `batch` slots, ONE selection and ONE backtrack launch per wave (CTA per (slot,
+    radius)), one host wait per wave; a subproblem with a non-integer u_old is reported for itself only."""
+    insts, df_all, uo_all = _multi_case(gpu_lib)
+    uo_all = uo_all.copy()
+    uo_all[4, 7, 1] = 0.5                                   # InexactError for subproblem 4 only
+    base = insts[0]
+    plan = gpu_lib.TRMPlan(base.nu, base.iterator, base.n, base.B, 0.25, 1, base.dt, batch=4)
+    radii = [99, 49, 24, 0]
+    launches0 = plan.stats()["launches"]
+    u_all, phi, bs, ks, status = plan.solve_batched(df_all, uo_all, radii, strict=False)
+    st = plan.stats()
+    assert st["batch_waves"] == 3 and st["batch_syncs"] == 3                # ceil(9 / 4) waves, one wait each
+    assert st["launches"] - launches0 == 3 * 3 + 9                           # per wave: DP + selection + backtrack; + one prep per subproblem
+    assert (status[4] == gpu_lib._lib.ERR_INEXACT).all() and (np.delete(status, 4, axis=0) == 0).all()
+    for s, inst in enumerate(insts):
+        if s == 4:
+            continue
+        U, Phi, _ = oracle_tables(oracle, inst.nu, inst.iterator, inst.n, inst.B, inst.df, inst.u_old, 0.25, 1, inst.dt, plan.cost)
+        for r, Bn in enumerate(radii):
+            ur = np.zeros((inst.n, 3))
+            info = {}
+            oracle.eval_u_TRM(ur, inst.u_old, U, Phi, Bn, inst.nu, info=info)
+            np.testing.assert_array_equal(u_all[s, r], ur)
+            assert phi[s, r] == info["phi_star"] and bs[s, r] == info["b_star"]
+    with pytest.raises(gpu_lib.InexactError):                               # strict mode raises the worst entry
+        plan.solve_batched(df_all, uo_all, radii)
+    plan.close()
+
+
+def test_multi_gpu_behind_the_c_abi(gpu_lib, oracle):
+    """bb200_multi_*: one ccall drives every visible GPU -- subproblem s on device s mod G, NCCL all-gather of the
+    16-byte best-candidate records inside the library, the winner's trajectory returned.  With one GPU the same entry
+    point runs without NCCL."""
+    G = min(gpu_lib.device_count(), 8)
+    insts, df_all, uo_all = _multi_case(gpu_lib, S=11)
+    base = insts[0]
+    mp = gpu_lib.MultiPlan(list(range(G)), base.nu, base.iterator, base.n, base.B, 0.25, 1, base.dt, batch_per_device=2)
+    radii = [99, 49, 24]
+    res = mp.solve_batched(df_all, uo_all, radii)
+    best = (np.inf, -1, -1)
+    for s, inst in enumerate(insts):
+        U, Phi, _ = oracle_tables(oracle, inst.nu, inst.iterator, inst.n, inst.B, inst.df, inst.u_old, 0.25, 1, inst.dt, mp.cost)
+        for r, Bn in enumerate(radii):
+            ur = np.zeros((inst.n, 3))
+            info = {}
+            oracle.eval_u_TRM(ur, inst.u_old, U, Phi, Bn, inst.nu, info=info)
+            np.testing.assert_array_equal(res["u"][s, r], ur)
+            assert res["phi"][s, r] == info["phi_star"]
+            if info["phi_star"] < best[0]:
+                best = (info["phi_star"], s, r)
+    assert (res["best_value"], res["best_subproblem"], res["best_radius"]) == best
+    np.testing.assert_array_equal(res["u_best"], res["u"][best[1], best[2]])
+    # without the trajectories: the winner's u is recomputed on its device
+    res2 = mp.solve_batched(df_all, uo_all, radii, want_u=False)
+    np.testing.assert_array_equal(res2["u_best"], res["u_best"])
+    assert mp.stats()["devices"] == G
+    if G > 1:
+        assert gpu_lib.nccl_version() > 0
+    mp.close()

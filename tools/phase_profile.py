@@ -32,6 +32,10 @@ def line(row):
             " | scatter: " + " ".join(f"{nm}={row[5+k]/stg:7.0f}" for k, nm in enumerate(names_s)) +
             " (" + " ".join(f"{nm}={row[14+k]/stg:6.0f}" for k, nm in enumerate(names_x)) + ")" +
             f" ring_wait={row[13]/stg:6.0f}" + " | comm/stage: " + " ".join(f"{nm}={row[8+k]/stg:6.2f}" for k, nm in enumerate(names_m)))
+if st.get("prune_block", 0):
+    print("pruned tiles: the scatter fields hold the sub-phases of the scan (warp 0): wait_scan = block minima + seed, wait_halo_ring = upper "
+          "bounds, phaseC = masks, C_combine = scan of the surviving blocks, C_store = blocks scanned; "
+          f"executed fraction of the launch = {st['executed_updates'] / plan.count_updates():.3f}")
 for gsel in sorted({0, 1, 2, G // 2, G - 2, G - 1}):
     if 0 <= gsel < G:
         print(f"cta {gsel:3d} " + line(prof[gsel]))
