@@ -39,7 +39,9 @@ extern "C" {
 #define BB200_ERR_ARG 1      /* invalid argument / shape                                           */
 #define BB200_ERR_CUDA 2     /* CUDA runtime failure (message has the CUDA error string)           */
 #define BB200_ERR_INEXACT 3  /* u_old not integer valued / not finite: Julia's InexactError,       */
-                             /* HelpFunctions.jl:37,57 (convert(Int64, abs(numl - u_old[m,i])))    */
+                             /* HelpFunctions.jl:37,57 (convert(Int64, abs(numl - u_old[m,i])));   */
+                             /* control levels are integers by type (the reference's nu is         */
+                             /* Vector{Vector{Int64}}, multi-trust.jl:64): level_values is int32   */
 #define BB200_ERR_STALE 4    /* selection/backtrack reached a cell the DP never wrote (the          */
                              /* reference would read stale U there)                     */
 #define BB200_ERR_STATE 5    /* call order violated (e.g. backtrack before any DP)                 */
@@ -204,8 +206,14 @@ int bb200_export_argmin(bb200_plan *plan, int32_t slot, int64_t i0, int64_t i1, 
 int bb200_count_updates(bb200_plan *plan, int32_t slot, int64_t *n_updates);
 
 /* Device-side "next" rows: evaluated on the resident u / u_old / df of `slot`.
- *   pred integral Δt·Σ_j ∇f[:,j]'(u_old[:,j]-u[:,j])  (multi-trust.jl:117-121)
- *   TV_p(u, p)  with p = +Inf, 1 or 2                    (HelpFunctions.jl:251-268)          */
+ *   pred integral Δt·Σ_j ∇f[:,j]'(u_old[:,j]-u[:,j])  (multi-trust.jl:117-121); the sum runs left to right over j and,
+ *       inside a column, over m -- the reference's `∇f[:,j]' * (..)` is a BLAS dot whose internal order is not
+ *       specified, so for M > 2 the last bit of `pred` is only pinned against this order
+ *   TV_p(u, p)  with p = +Inf, 1 or 2                    (HelpFunctions.jl:251-268)
+ *       p = 1 and p = Inf are bit-exact (integer-valued u: every term is exact).  p = 2 is NOT bit-pinned: the
+ *       reference evaluates (Σ|Δ|^2)^(1/p) with Julia's Float64 `^`, this kernel uses sqrt -- identical whenever the
+ *       sum is a perfect square, otherwise possibly one ulp apart.  Callers who need the reference's bits for p = 2
+ *       keep TV_p in Julia (it is O(M·n)). */
 int bb200_pred_integral(bb200_plan *plan, int32_t slot, double *int_val);
 int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
 

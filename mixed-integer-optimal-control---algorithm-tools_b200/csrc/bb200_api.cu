@@ -117,6 +117,18 @@ struct bb200_plan {
 
 namespace {
 
+// Watchdog of the persistent kernel's inter-CTA waits: seconds from $BELLMAN_B200_WATCHDOG_S (default 3; 0 disables it
+// for runs under a debugger / compute-sanitizer / on a time-sliced GPU), converted with the nominal 2 GHz clock.
+long long watchdog_cycles()
+{
+    static const long long v = [] {
+        const char *e = getenv("BELLMAN_B200_WATCHDOG_S");
+        const double sec = e ? atof(e) : 3.0;
+        return sec <= 0. ? 0LL : (long long)(sec * 2.0e9);
+    }();
+    return v;
+}
+
 int decouple_env()
 {
     static const int v = [] { const char *e = getenv("BELLMAN_B200_DECOUPLE"); return e ? atoi(e) : 0; }();
@@ -133,6 +145,28 @@ int dev_alloc(bb200_plan *p, T **ptr, size_t count)
         return fail(BB200_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     p->dev_bytes += bytes;
     return BB200_OK;
+}
+
+// The halo ring (a few tens of MB) is re-read every stage while the argmin table streams through L2 once: ask the
+// driver to keep the ring's lines (persisting access-policy window on the plan's stream; best effort).
+void pin_ring_in_l2(bb200_plan *p)
+{
+    if (!p->d_halo || !p->stream) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) { cudaGetLastError(); return; }
+    const size_t bytes = p->halo_elems * sizeof(double);
+    const size_t win = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+    if (win == 0 || prop.persistingL2CacheMaxSize == 0) return;
+    const size_t want = win < (size_t)prop.persistingL2CacheMaxSize ? win : (size_t)prop.persistingL2CacheMaxSize;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = p->d_halo;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(p->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();  // best effort: a refusal changes traffic, not results
 }
 
 int reconfigure(bb200_plan *p)
@@ -161,9 +195,17 @@ int reconfigure(bb200_plan *p)
             }
             p->halo_elems = need;
             p->dev_bytes += need * sizeof(double);
+            // pad columns of the ring rows are never written by a kernel but travel with the rows (bulk TMA) and are read
+            // by the pruned scan's block minima: give them a huge finite value (0x7f7f.. = 1.4e306) instead of whatever the
+            // allocation held
+            if (cudaMemset(p->d_halo, 0x7f, need * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(BB200_ERR_CUDA, "cudaMemset of the halo ring failed");
+            }
         }
         p->cfg = c;
         p->wave_ok = true;
+        pin_ring_in_l2(p);
     }
     return BB200_OK;
 }
@@ -245,6 +287,7 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false, cudaEv
             c.btmax = p->d_btmax;
             c.prof = p->prof_on ? p->d_prof : nullptr;
             c.exec = p->d_exec;
+            c.wd_cycles = watchdog_cycles();
             c.decouple = p->prof_on ? decouple_env() : 0;  // profiling experiment (PROF instantiation only), never a result
             CU(launch_wavefront(p->tab, c, p->argw, st));
             done += chunk;
@@ -513,6 +556,8 @@ int bb200_plan_set_stream(bb200_plan *plan, void *cuda_stream)
     Guard g(plan);
     CU(cudaStreamSynchronize(plan->stream));
     plan->stream = cuda_stream ? (cudaStream_t)cuda_stream : plan->own_stream;
+    if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }  // captured on the old stream
+    if (plan->wave_ok) pin_ring_in_l2(plan);
     return BB200_OK;
 }
 

@@ -99,7 +99,7 @@ __device__ __forceinline__ bool reached(unsigned int cnt, unsigned int want) { r
 // mbarrier wait with a watchdog: a lost hand-over becomes an error code (err[2] watchdog, err[3] abort) instead of
 // a hung GPU.  Once the abort flag is up every wait gives up quickly so that the launch drains.  The waiting loop is
 // ONE out-of-line copy: the kernel's hot code has to stay below the 32 KB instruction-cache tier.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int *err)
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, int *err, long long wd_cycles)
 {
     unsigned int spins = 0;
     long long t0 = 0;
@@ -120,7 +120,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, 
             if (t0 == 0) t0 = now;
             if (*(volatile int *)&err[3]) {
                 if (spins >= 256u) return;
-            } else if (now - t0 > 6000000000LL) {  // ~3 s
+            } else if (wd_cycles > 0 && now - t0 > wd_cycles) {  // default ~3 s; 0 disables (debugger, sanitizer, time slicing)
                 atomicOr(&err[2], 2);
                 atomicOr(&err[3], 1);
                 return;
@@ -128,10 +128,10 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, 
         }
     }
 }
-__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int *err)
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int *err, long long wd_cycles = 6000000000LL)
 {
     if (mbar_test(bar, parity)) return;
-    mbar_wait_slow(smem_u32(bar), parity, err);
+    mbar_wait_slow(smem_u32(bar), parity, err, wd_cycles);
 }
 
 #ifndef BB_COMM_SLEEP
@@ -315,117 +315,146 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 template <int TB, int BK, typename ArgT, bool PROF>
 __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
                                             const double *__restrict__ cm_l, double *__restrict__ pm,
-                                            double *__restrict__ pmm, double s, int nblk, int Kp, bool live, int lane,
-                                            double (&best)[TB][1], int (&arg)[TB][1], unsigned int &executed,
+                                            double *__restrict__ pmm, double s, int nblk, int Kp, bool live, int rows_live,
+                                            int lane, double (&best)[TB][1], int (&arg)[TB][1], unsigned int &executed,
                                             long long (&ph)[4])
 {
+    // An FP64 add / compare has a latency of ~40 cycles on sm_100a and a CTA runs two of these warps per scheduler:
+    // every phase below is written as independent chains (register arrays filled first, compared afterwards), never
+    // as a load -> add -> compare -> branch chain per block.
+    static_assert(TB <= 4 && BK == 4, "block minima are stored four rows wide; the scan takes two successor pairs per block");
+    constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
+    const double inf = d_inf();
     long long tq = 0;
     if constexpr (PROF) tq = clock64();
 #define PH_LAP(k) do { if constexpr (PROF) { const long long tn = clock64(); ph[k] += tn - tq; tq = tn; } } while (0)
-    static_assert(TB <= 4 && BK % 2 == 0, "block minima are stored four rows wide; successors are taken in pairs");
-    constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
-    const double inf = d_inf();
-    // ---- 1. block minima (lane = block) and the seed block ---------------------------------------------------
-    double myv = inf;
-    int myq = lane;
+    // ---- 1. block minima (lane = block; nblk is a multiple of 8, at most 32) and the seed block ---------------
+    unsigned int key = 0xffffffffu;
     if (lane < nblk) {
-        double mall = inf;
+        double m[TB];
 #pragma unroll
         for (int r = 0; r < TB; ++r) {
-            double m = inf;
-#pragma unroll
-            for (int jj = 0; jj < BK; jj += 2) {
-                const double2 w = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK + jj);
-                m = fmin(m, fmin(w.x, w.y));
-            }
-            pm[4 * lane + r] = m;
-            mall = fmin(mall, m);
+            const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK);
+            const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK + 2);
+            m[r] = fmin(fmin(w0.x, w0.y), fmin(w1.x, w1.y));
         }
-        pmm[lane] = mall;
-        myv = mall;
-    }
+        double mall = m[0];
 #pragma unroll
-    for (int w = 16; w > 0; w >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, myv, w);
-        const int oq = __shfl_xor_sync(0xffffffffu, myq, w);
-        if (ov < myv || (ov == myv && oq < myq)) { myv = ov; myq = oq; }
+        for (int r = 1; r < TB; ++r) mall = fmin(mall, m[r]);
+#pragma unroll
+        for (int r = 0; r < TB; ++r) pm[4 * lane + r] = m[r];
+        pmm[lane] = mall;
+        // seed = a block with a (nearly) smallest merged minimum: any block gives valid bounds, so a 27-bit order-
+        // preserving key of the minimum (rounded down to float) with the lane in the low bits is enough
+        const unsigned int u = __float_as_uint(__double2float_rd(mall));
+        key = (((u & 0x80000000u) ? ~u : (u | 0x80000000u)) & ~31u) | (unsigned int)lane;
     }
-    const int qs = min(myq, nblk - 1);  // warp-uniform
+    const int qs = (int)(__reduce_min_sync(0xffffffffu, key) & 31u);  // warp-uniform; also orders the pm / pmm writes
     __syncwarp();
     PH_LAP(0);
     // ---- 2. upper bounds from the seed block (values only) ---------------------------------------------------
     double ub[TB];
+    {
+        double a[BK];
 #pragma unroll
-    for (int r = 0; r < TB; ++r) ub[r] = inf;
-#pragma unroll
-    for (int jj = 0; jj < BK; jj += 2) {
-        const int j = qs * BK + jj;
-        const double a0 = __dadd_rn(s, cs_l[(size_t)j * Kp]);
-        const double a1 = __dadd_rn(s, cs_l[(size_t)(j + 1) * Kp]);
+        for (int jj = 0; jj < BK; ++jj) a[jj] = __dadd_rn(s, cs_l[(size_t)(qs * BK + jj) * Kp]);
 #pragma unroll
         for (int r = 0; r < TB; ++r) {
-            const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + j);
-            const double v0 = __dadd_rn(a0, x.x), v1 = __dadd_rn(a1, x.y);
-            if (ub[r] > v0) ub[r] = v0;
-            if (ub[r] > v1) ub[r] = v1;
+            const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs * BK);
+            const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs * BK + 2);
+            const double v0 = __dadd_rn(a[0], w0.x), v1 = __dadd_rn(a[1], w0.y), v2 = __dadd_rn(a[2], w1.x), v3 = __dadd_rn(a[3], w1.y);
+            double u01 = inf, u23 = inf;               // from +Inf with '>', so that a NaN candidate is ignored
+            if (u01 > v0) u01 = v0;
+            if (u23 > v2) u23 = v2;
+            if (u01 > v1) u01 = v1;
+            if (u23 > v3) u23 = v3;
+            ub[r] = u01 > u23 ? u23 : u01;
+            if (!live || r >= rows_live) ub[r] = -inf;  // pad levels and rows beyond the table never ask for a block
         }
     }
-    double ubmax = -inf;
+    double ubmax = ub[0];
 #pragma unroll
-    for (int r = 0; r < TB; ++r) {
-        if (!live) ub[r] = -inf;  // idle lanes (pad levels) never ask for a block
-        if (ub[r] > ubmax) ubmax = ub[r];
-    }
+    for (int r = 1; r < TB; ++r) ubmax = ub[r] > ubmax ? ub[r] : ubmax;
     PH_LAP(1);
     // ---- 3. which blocks can hold a minimum of some cell of this warp? --------------------------------------
     unsigned int mneed = 0;
-#pragma unroll 4
-    for (int q = 0; q < nblk; ++q) {
-        const double lb = __dadd_rn(__dadd_rn(s, cm_l[(size_t)q * Kp]), pmm[q]);
-        mneed |= (lb > ubmax ? 0u : 1u) << q;
-    }
-    unsigned int pneed = 0;
-    for (unsigned int m = __reduce_or_sync(0xffffffffu, mneed); m; m &= m - 1) {
-        const int q = __ffs(m) - 1;
-        const double amin = __dadd_rn(s, cm_l[(size_t)q * Kp]);
-        const double2 x = *reinterpret_cast<const double2 *>(pm + 4 * q);
-        const double2 y = *reinterpret_cast<const double2 *>(pm + 4 * q + 2);
-        const double pmq[4] = {x.x, x.y, y.x, y.y};
-        bool nd = false;
+#pragma unroll 1
+    for (int q0 = 0; q0 < nblk; q0 += 16) {  // cheap test, merged over the warp's rows: 16 independent chains per trip
+        double lb[16];
 #pragma unroll
-        for (int r = 0; r < TB; ++r) nd = nd || !(__dadd_rn(amin, pmq[r]) > ub[r]);
-        pneed |= (nd ? 1u : 0u) << q;
+        for (int k = 0; k < 16; ++k) {
+            const int q = min(q0 + k, nblk - 1);
+            lb[k] = __dadd_rn(__dadd_rn(s, cm_l[(size_t)q * Kp]), pmm[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) mneed |= ((lb[k] > ubmax || q0 + k >= nblk) ? 0u : 1u) << ((q0 + k) & 31);
     }
+    const unsigned int m1 = __reduce_or_sync(0xffffffffu, mneed);
+    unsigned int pneed = 0;
+#pragma unroll 1
+    for (int q0 = 0; q0 < nblk; q0 += 8) {  // exact test per row, eight blocks at a time, only where the cheap test said "maybe"
+        if (((m1 >> q0) & 0xffu) == 0u) continue;
+        double lbr[8][TB];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double amin = __dadd_rn(s, cm_l[(size_t)(q0 + k) * Kp]);
+            const double2 x = *reinterpret_cast<const double2 *>(pm + 4 * (q0 + k));
+            const double2 y = *reinterpret_cast<const double2 *>(pm + 4 * (q0 + k) + 2);
+            const double pmq[4] = {x.x, x.y, y.x, y.y};
+#pragma unroll
+            for (int r = 0; r < TB; ++r) lbr[k][r] = __dadd_rn(amin, pmq[r]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bool nd = false;
+#pragma unroll
+            for (int r = 0; r < TB; ++r) nd = nd || !(lbr[k][r] > ub[r]);
+            pneed |= (nd ? 1u : 0u) << (q0 + k);
+        }
+    }
+    unsigned int m2 = __reduce_or_sync(0xffffffffu, pneed & m1);
+    PH_LAP(2);
     // ---- 4. exhaustive scan of the surviving blocks, ascending, strict '>' -----------------------------------
+    // The candidates of the NEXT surviving block are loaded and added while the compare -> move chain of the current
+    // one runs (the chain through `best` is the only true dependency between blocks).
 #pragma unroll
     for (int r = 0; r < TB; ++r) { best[r][0] = inf; arg[r][0] = MARKI; }
-    unsigned int mfinal = __reduce_or_sync(0xffffffffu, pneed);
-    PH_LAP(2);
-    for (unsigned int m = mfinal; m; m &= m - 1) {
-        const int j0 = (__ffs(m) - 1) * BK;
-        executed += 1;
+    auto candidates = [&](int q, double (&v)[TB][BK]) {
+        double a[BK];
 #pragma unroll
-        for (int jj = 0; jj < BK; jj += 2) {
-            const int j = j0 + jj;
-            double p0[TB], p1[TB];
+        for (int jj = 0; jj < BK; ++jj) a[jj] = __dadd_rn(s, cs_l[(size_t)(q * BK + jj) * Kp]);   // HelpFunctions.jl:67
 #pragma unroll
-            for (int r = 0; r < TB; ++r) {
-                const double2 x = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + j);
-                p0[r] = x.x;
-                p1[r] = x.y;
-            }
-            const double a0 = __dadd_rn(s, cs_l[(size_t)j * Kp]);        // HelpFunctions.jl:67
-            const double a1 = __dadd_rn(s, cs_l[(size_t)(j + 1) * Kp]);
+        for (int r = 0; r < TB; ++r) {
+            const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + q * BK);
+            const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + q * BK + 2);
+            v[r][0] = __dadd_rn(a[0], w0.x);                                                        // :71
+            v[r][1] = __dadd_rn(a[1], w0.y);
+            v[r][2] = __dadd_rn(a[2], w1.x);
+            v[r][3] = __dadd_rn(a[3], w1.y);
+        }
+    };
+    if (m2) {
+        double vc[TB][BK];
+        int q = __ffs(m2) - 1;
+        m2 &= m2 - 1;
+        candidates(q, vc);
+        for (;;) {
+            double vn[TB][BK];
+            const int qn = m2 ? __ffs(m2) - 1 : -1;
+            m2 &= m2 - 1;
+            if (qn >= 0) candidates(qn, vn);
+            executed += 1;
 #pragma unroll
-            for (int r = 0; r < TB; ++r) {
-                const double v = __dadd_rn(a0, p0[r]);                                 // :71
-                if (best[r][0] > v) { BB_KEEP_BRANCH; best[r][0] = v; arg[r][0] = j; }  // :73-76
-            }
+            for (int jj = 0; jj < BK; ++jj)
 #pragma unroll
-            for (int r = 0; r < TB; ++r) {
-                const double v = __dadd_rn(a1, p1[r]);
-                if (best[r][0] > v) { BB_KEEP_BRANCH; best[r][0] = v; arg[r][0] = j + 1; }
-            }
+                for (int r = 0; r < TB; ++r)
+                    if (best[r][0] > vc[r][jj]) { BB_KEEP_BRANCH; best[r][0] = vc[r][jj]; arg[r][0] = q * BK + jj; }  // :73-76
+            if (qn < 0) break;
+#pragma unroll
+            for (int r = 0; r < TB; ++r)
+#pragma unroll
+                for (int jj = 0; jj < BK; ++jj) vc[r][jj] = vn[r][jj];
+            q = qn;
         }
     }
     PH_LAP(3);
@@ -566,7 +595,7 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
 #pragma unroll
         for (int e = 0; e < EC; ++e) {
             if (no_src[e]) Pn[x + e] = inf;
-            if (ok[e]) argrow[x + e] = (unsigned char)arg[e];
+            if (ok[e]) __stcs(argrow + x + e, (unsigned char)arg[e]);  // written once, streamed: do not displace the ring in L2
             if (ok[e] && y[e] < RK) Pn[y[e]] = val[e];
             if (ok[e] && y[e] >= RK) hring[y[e]] = val[e];
         }
@@ -601,7 +630,7 @@ __device__ __forceinline__ void scatter_tile(const FinishArgs &a, int row0, int 
             const int y = x + bt * a.Kp;
             if (in_tab && a.r0 + row < bt) a.Pn[x] = inf;  // no source row: +Inf (:47)
             if (in_tab && row + bt < rows_left) {           // inside `for b = 0:B-b~` (:69)
-                argrow[x] = (ArgT)arg[r][q];
+                __stcs(argrow + x, (ArgT)arg[r][q]);  // written once, streamed: do not displace the ring in L2
                 if (y < RK) a.Pn[y] = best[r][q];
                 else a.hring[y] = best[r][q];
                 if (a.phi) a.phi[y] = best[r][q];
@@ -659,7 +688,7 @@ struct Finisher {
         // my next rows receive the lower slices' block by TMA (issued by the comm warp): it must have landed before
         // my own results overwrite the cells I produce myself
         if (halo_on && i >= 2) {
-            mbar_wait_wd(&sm.mbar[MB_HALO + (i & 1)], (halo_phase >> (i & 1)) & 1u, c.err);
+            mbar_wait_wd(&sm.mbar[MB_HALO + (i & 1)], (halo_phase >> (i & 1)) & 1u, c.err, c.wd_cycles);
             halo_phase ^= 1u << (i & 1);
         }
         // back-pressure: the successors consumed the ring slot this step overwrites
@@ -719,7 +748,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
 #define PROF_LAP(k) do { if constexpr (PROF) { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } } while (0)
     auto wait_costs = [&](int T) {
         const int b = (int)(T % 3);
-        mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err);
+        mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err, c.wd_cycles);
         cost_phase ^= 1u << b;
     };
     auto finished = [&](int v) {
@@ -745,7 +774,7 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
             fin.wait_inputs(i, T);
             PROF_LAP(1);
             for (int v = 0; v < NV; ++v) {
-                mbar_wait_wd(&sm.mbar[MB_SCANNED + v], (scanned_phase >> v) & 1u, c.err);
+                mbar_wait_wd(&sm.mbar[MB_SCANNED + v], (scanned_phase >> v) & 1u, c.err, c.wd_cycles);
                 scanned_phase ^= 1u << v;
                 PROF_LAP(0);
                 const int ub = v == 0 ? 0 : c.RA * ublocks, ue = v == 0 ? c.RA * ublocks : R * ublocks;
@@ -882,7 +911,7 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
         pc[1] += 1;
         if ((++idle & 0x3ffu) == 0) {
             bool abort_now = *(volatile int *)&c.err[3] != 0;
-            if (!abort_now && idle > (1u << 22)) {
+            if (!abort_now && c.wd_cycles > 0 && idle > (1u << 22)) {
                 atomicOr(&c.err[2], 1);
                 atomicOr(&c.err[3], 1);
                 abort_now = true;
@@ -1008,11 +1037,11 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 #define PROF_LAP(k) do { if constexpr (PROF) { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } } while (0)
     auto wait_costs = [&](int T) {
         const int b = (int)(T % 3);
-        mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err);
+        mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err, c.wd_cycles);
         cost_phase ^= 1u << b;
     };
     auto wait_finished = [&](int v) {
-        mbar_wait_wd(&sm.mbar[MB_FINISHED + v], (fin_phase >> v) & 1u, c.err);
+        mbar_wait_wd(&sm.mbar[MB_FINISHED + v], (fin_phase >> v) & 1u, c.err, c.wd_cycles);
         fin_phase ^= 1u << v;
     };
     auto scanned = [&](int v) {
@@ -1066,7 +1095,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 if (pr_grp == 0) {
                     double best[TBA][1];
                     int arg[TBA][1];
-                    scan_pruned<TBA, PR, ArgT, PROF>(Pc, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, lane, best, arg, executed, ph);
+                    scan_pruned<TBA, PR, ArgT, PROF>(Pc, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, t.B1 - fin.r0, lane, best, arg, executed, ph);
                     PROF_LAP(1);
                     scanned(0);  // the comm warp may refill the rows this stage read
                     fin.wait_inputs(i, T);
@@ -1075,7 +1104,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 } else if constexpr (TBB > 0) {
                     double best[TBB][1];
                     int arg[TBB][1];
-                    scan_pruned<TBB, PR, ArgT, PROF>(Pc + (size_t)TBA * Kp, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, lane, best, arg, executed, ph);
+                    scan_pruned<TBB, PR, ArgT, PROF>(Pc + (size_t)TBA * Kp, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, t.B1 - fin.r0 - TBA, lane, best, arg, executed, ph);
                     PROF_LAP(1);
                     scanned(0);
                     fin.wait_inputs(i, T);
@@ -1120,7 +1149,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 PROF_LAP(2);
             } else if (self_finish) {
                 // ---- phase C by the compute warps: all partial minima are in shared memory once every warp scanned
-                mbar_wait_wd(&sm.mbar[MB_SCANNED], scanned_phase, c.err);
+                mbar_wait_wd(&sm.mbar[MB_SCANNED], scanned_phase, c.err, c.wd_cycles);
                 scanned_phase ^= 1u;
                 fin.wait_inputs(i, T);
                 PROF_LAP(2);
@@ -1175,7 +1204,7 @@ struct Variant { int TBA, TBB, TL, PR; };
     X(8, 8, 0, 1, 0) X(9, 4, 0, 1, 0) X(10, 2, 0, 1, 0) X(11, 1, 0, 1, 0)                                                    \
     X(12, 4, 3, 2, 0) X(13, 4, 4, 2, 0) X(14, 3, 3, 2, 0) X(15, 3, 2, 2, 0) X(16, 2, 2, 2, 0) X(17, 2, 1, 2, 0) X(18, 1, 1, 2, 0)     \
     X(19, 4, 4, 1, 0) X(20, 2, 2, 1, 0) X(21, 1, 1, 1, 0) X(22, 4, 3, 1, 0) X(23, 3, 3, 1, 0)                               \
-    X(24, 4, 3, 1, 4) X(25, 4, 3, 1, 8) X(26, 4, 4, 1, 4) X(27, 3, 3, 1, 4) X(28, 2, 2, 1, 4) X(29, 1, 1, 1, 4) X(30, 4, 0, 1, 4) X(31, 2, 0, 1, 4)
+    X(24, 4, 3, 1, 4) X(25, 3, 2, 1, 4) X(26, 4, 4, 1, 4) X(27, 3, 3, 1, 4) X(28, 2, 2, 1, 4) X(29, 1, 1, 1, 4) X(30, 4, 0, 1, 4) X(31, 2, 0, 1, 4)
 static const Variant kVariants[] = {
 #define X(idx, a, b, l, pr) {a, b, l, pr},
     BB200_VARIANTS(X)
@@ -1204,7 +1233,7 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int N
         c.G = (t.B1 + c.R - 1) / c.R;
         c.nLG = t.K;
         c.JS = 1;
-        c.jper = c.Kr = (t.K + c.PR - 1) / c.PR * c.PR;  // whole blocks; rows K .. Kr-1 of the cost table are +Inf
+        c.jper = c.Kr = (t.K + 8 * c.PR - 1) / (8 * c.PR) * (8 * c.PR);  // whole groups of eight blocks; rows K .. Kr-1 of the cost table are +Inf
         c.tpg = t.Kp * (c.TBB > 0 ? 2 : 1);              // 32 lanes per level block and row group
         c.NS = 0;
         c.EC = 2;
@@ -1255,7 +1284,7 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
         if (pr > 0) {
             // the pruned scan pays when a stage has many successors to skip; narrow level sets keep the exhaustive tiles
             if (want_variant == 0 && (!kAutoPruned || t.K < 64)) continue;
-            if ((t.K + pr - 1) / pr * pr > t.Kp || (t.K + pr - 1) / pr > 32) continue;  // whole blocks, one mask word
+            if ((t.K + 8 * pr - 1) / (8 * pr) * (8 * pr) > t.Kp || (t.K + 8 * pr - 1) / (8 * pr) * 8 > 32) continue;  // whole groups of eight blocks, one mask word
         }
         for (int js = 1; js <= 16; ++js) {
             if (want_js > 0 && js != want_js) continue;

@@ -46,6 +46,7 @@ struct WaveCfg {
     long long *prof;             // optional [G][16] cycle counters (NULL = off)
     unsigned long long *exec;    // pruned scan: number of candidates actually evaluated by this launch (all CTAs)
     int decouple;                // timing experiments only: CTAs ignore their neighbours (wrong results)
+    long long wd_cycles;         // watchdog of the inter-CTA waits in SM cycles (0 = off); $BELLMAN_B200_WATCHDOG_S, default 3 s
 };
 
 // Fills the geometry fields of cfg for the given tables; returns false when the shape cannot run on the
