@@ -72,6 +72,10 @@ struct bb200_plan {
     unsigned long long *d_flags = nullptr;
     int *d_err = nullptr, *d_btmax = nullptr;
     unsigned long long *d_exec = nullptr;  // pruned scan: candidates really evaluated by the last DP
+    unsigned long long *h_exec = nullptr;  // pinned copy, fetched with the error words
+    int last_dp_slots = 1;                 // slots of the last DP launch (the counter above sums over them)
+    bool prune_off = false;                // the pruned scan did not pay on this plan's data: exhaustive tiles from now on
+    double prune_switches = 0.;
     long long *d_prof = nullptr;
     bool prof_on = false;
     SlotDev *d_slots = nullptr;
@@ -181,7 +185,8 @@ int reconfigure(bb200_plan *p)
         return BB200_OK;
     }
     WaveCfg c{};
-    if (wave_configure(p->tab, p->argw, p->num_sms, p->smem_max, p->tune_ctas, p->tune_js, p->tune_variant, c)) {
+    const int want_variant = (p->prune_off && p->tune_variant == 0) ? -1 : p->tune_variant;
+    if (wave_configure(p->tab, p->argw, p->num_sms, p->smem_max, p->tune_ctas, p->tune_js, want_variant, c)) {
         // the halo ring holds kHaloRing stages of value rows [B1][Kp], row-major like the rows in shared memory
         const size_t need = (size_t)kHaloRing * p->B1 * p->Kp;
         if (need > p->halo_elems) {
@@ -238,6 +243,7 @@ void destroy_plan(bb200_plan *p)
     cudaFree(p->d_prof);
     if (p->h_rec) cudaFreeHost(p->h_rec);
     if (p->h_err) cudaFreeHost(p->h_err);
+    if (p->h_exec) cudaFreeHost(p->h_exec);
     if (p->h_df) cudaFreeHost(p->h_df);
     if (p->h_uold) cudaFreeHost(p->h_uold);
     if (p->h_u) cudaFreeHost(p->h_u);
@@ -258,6 +264,7 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false, cudaEv
     CU(cudaMemsetAsync(p->d_btmax, 0, sizeof(int), st));
     CU(cudaMemsetAsync(p->d_exec, 0, sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(p->d_rec_all + (size_t)slot0 * kRecDoubles, 0, (size_t)count * kRecDoubles * sizeof(double), st));
+    p->last_dp_slots = count;
     for (int s = slot0; s < slot0 + count; ++s) {
         CU(cudaMemsetAsync(p->slots[s].n_updates, 0, sizeof(unsigned long long), st));
         launch_prep(p->tab, p->slots_dev[s], p->d_err, p->d_btmax, st);
@@ -360,7 +367,8 @@ bool ensure_graph(bb200_plan *p)
              queue_dp(p, 0, 1, true) == BB200_OK && queue_backtrack(p, 0, p->B, 0, true) == BB200_OK &&
              cudaMemcpyAsync(p->h_u, p->slots[0].u, io, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
              cudaMemcpyAsync(p->h_rec, p->slots[0].rec, 4 * sizeof(double), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-             cudaMemcpyAsync(p->h_err, p->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+             cudaMemcpyAsync(p->h_err, p->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaMemcpyAsync(p->h_exec, p->d_exec, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) == cudaSuccess;
         cudaError_t e = cudaStreamEndCapture(st, &graph);
         ok = ok && e == cudaSuccess && graph != nullptr;
     }
@@ -376,11 +384,28 @@ bool ensure_graph(bb200_plan *p)
     return ok;
 }
 
+// The pruned scan only pays when its bound test drops most blocks; that depends on the data (jump costs against the
+// spread of the value rows).  After a synchronised DP: if more than 60 % of the candidates were evaluated anyway, this
+// plan goes back to the exhaustive tiles for its following DPs (TRM calls the DP again and again on similar data).
+void adapt_pruning(bb200_plan *p, int slots)
+{
+    if (!p->wave_ok || p->cfg.PR == 0 || p->tune_variant != 0 || p->prune_off) return;
+    const double full = (double)(p->n > 1 ? p->n - 1 : 1) * p->B1 * (double)p->cfg.Kr * p->K * slots;
+    if ((double)*p->h_exec > 0.6 * full) {
+        p->prune_off = true;
+        p->prune_switches += 1;
+        if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }  // geometry is baked in
+        reconfigure(p);
+    }
+}
+
 // Synchronise and translate the deferred device-side error word.
 int sync_and_check(bb200_plan *p)
 {
     CU(cudaMemcpyAsync(p->h_err, p->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_exec, p->d_exec, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
+    if (p->dp_timed) adapt_pruning(p, p->last_dp_slots);
     if (p->dp_timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->last_dp_ms = ms;
@@ -537,6 +562,8 @@ int bb200_plan_create(int device, int64_t n, int32_t M, int32_t K, int64_t B, co
     CUB(cudaMallocHost((void **)&p->h_rec, kRecDoubles * sizeof(double)));
     CUB(cudaMemset(p->d_rec_all, 0, (size_t)batch * kRecDoubles * sizeof(double)));
     CUB(cudaMallocHost((void **)&p->h_err, 4 * sizeof(int)));
+    CUB(cudaMallocHost((void **)&p->h_exec, sizeof(unsigned long long)));
+    *p->h_exec = 0ull;
 #undef CUB
     if ((rc = reconfigure(p))) return bail(rc);
     *out = p;
@@ -705,6 +732,7 @@ int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t
         plan->launches += 4 + (one_launch ? 0 : (double)plan->n - 1);  // prep, DP, selection, backtrack
         plan->last_path = plan->mini_ok ? 2 : (plan->wave_ok ? 1 : 0);
         plan->graph_replays += 1;
+        adapt_pruning(plan, 1);
         std::memcpy(u_out, plan->h_u, io);
         if (phi_star) *phi_star = plan->h_rec[0];
         if (b_star) *b_star = (int64_t)plan->h_rec[1];
@@ -1066,15 +1094,15 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
         CU(cudaStreamSynchronize(plan->stream));
         CU(cudaMemcpy(&exec, plan->d_exec, sizeof exec, cudaMemcpyDeviceToHost));
     }
-    const double v[19] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+    const double v[20] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
                           plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
                           (double)plan->argw, (double)plan->dev_bytes,
                           plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.,
                           plan->last_wave_ms, plan->graph_replays,
                           plan->wave_ok ? (double)(plan->cfg.variant + 1) : 0., plan->wave_ok ? (double)plan->cfg.NS : 0.,
                           plan->last_batch_ms, plan->batch_waves, plan->batch_syncs, (double)exec,
-                          plan->wave_ok ? (double)plan->cfg.PR : 0.};
-    for (int k = 0; k < count && k < 19; ++k) out[k] = v[k];
+                          plan->wave_ok ? (double)plan->cfg.PR : 0., plan->prune_switches};
+    for (int k = 0; k < count && k < 20; ++k) out[k] = v[k];
     return BB200_OK;
 }
 

@@ -153,7 +153,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
 #define BB_KEEP_BRANCH
 #endif
 constexpr int kUnrollB = BB_UNROLL;  // successor pairs per trip of the phase-B loop
-constexpr bool kAutoPruned = false;  // may the geometry model pick pruned tiles by itself (wide level sets only)?
+constexpr bool kAutoPruned = true;  // may the geometry model pick pruned tiles by itself (wide level sets only)?
 constexpr int kNever = 0x7fffffff;  // "no bound": ticks are 32-bit, wave_configure refuses launches with >= 2^30 steps
 
 // shared-memory synchronisation words
@@ -178,7 +178,9 @@ struct Smem {
     unsigned char *pa;  // ArgT[JS*R*Kp] partial argmins
     int *umap;        // [R*ceil(Kp/64)] phase-C work unit -> (row << 16) | first level
     double *cmin;     // pruned scan: [Kr/PR][Kp] block minima of the jump costs, cmin[q][l] = min_{j in block q} c_jl
-    double *pmin;     // pruned scan: [compute warps][6 * Kr/PR] block minima of the warp's value rows ([Kr/PR][4] per row, [Kr/PR] merged, pad)
+    double *pmin;     // pruned scan: [compute warps][6 * Kr/PR] block minima of the warp's value rows ([Kr/PR][4] per row, then the
+                      //              super-block minima merged over the rows, pad)
+    double *cmins;    // pruned scan: [Kr/PR/4][Kp] super-block (4 blocks) minima of the jump costs
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -186,19 +188,21 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int argw, unsigned char *base, Smem *s)
 {
     size_t off = 0;
-    size_t o[10];
+    size_t o[11];
     const int nblk = c.PR ? c.Kr / c.PR : 0;
-    const size_t sizes[10] = {SYNC_WORDS * sizeof(uint64_t),
+    const int js_smem = c.PR ? 0 : c.JS;  // pruned tiles keep no partial minima in shared memory
+    const size_t sizes[11] = {SYNC_WORDS * sizeof(uint64_t),
                              3 * (size_t)t.Kp * sizeof(double),
                              3 * (size_t)t.Kp * sizeof(int),
                              2 * (size_t)t.Kp * c.R * sizeof(double),
                              (size_t)c.Kr * t.Kp * sizeof(double),
-                             (size_t)c.JS * c.R * t.Kp * sizeof(double),
-                             (size_t)c.JS * c.R * t.Kp * (size_t)argw,
+                             (size_t)js_smem * c.R * t.Kp * sizeof(double),
+                             (size_t)js_smem * c.R * t.Kp * (size_t)argw,
                              (size_t)c.R * (t.Kp / 32) * sizeof(int),
                              (size_t)nblk * t.Kp * sizeof(double),
-                             (size_t)(c.tpg / 32) * nblk * 6 * sizeof(double)};
-    for (int k = 0; k < 10; ++k) {
+                             (size_t)(c.tpg / 32) * nblk * 6 * sizeof(double),
+                             (size_t)(nblk / 4) * t.Kp * sizeof(double)};
+    for (int k = 0; k < 11; ++k) {
         o[k] = off;
         off = align_up(off + sizes[k], 128);
     }
@@ -213,6 +217,7 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
         s->umap = reinterpret_cast<int *>(base + o[7]);
         s->cmin = reinterpret_cast<double *>(base + o[8]);
         s->pmin = reinterpret_cast<double *>(base + o[9]);
+        s->cmins = reinterpret_cast<double *>(base + o[10]);
     }
     return off;
 }
@@ -314,22 +319,25 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 //      the same (earliest) argmin, bit for bit.
 template <int TB, int BK, typename ArgT, bool PROF>
 __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
-                                            const double *__restrict__ cm_l, double *__restrict__ pm,
-                                            double *__restrict__ pmm, double s, int nblk, int Kp, bool live, int rows_live,
-                                            int lane, double (&best)[TB][1], int (&arg)[TB][1], unsigned int &executed,
-                                            long long (&ph)[4])
+                                            const double *__restrict__ cm_l, const double *__restrict__ cms_l,
+                                            double *__restrict__ pm, double *__restrict__ pms, double s, int nblk, int Kp,
+                                            bool live, int rows_live, int lane, int l_self, double (&best)[TB][1],
+                                            int (&arg)[TB][1], unsigned int &executed, long long (&ph)[4])
 {
-    // An FP64 add / compare has a latency of ~40 cycles on sm_100a and a CTA runs two of these warps per scheduler:
-    // every phase below is written as independent chains (register arrays filled first, compared afterwards), never
-    // as a load -> add -> compare -> branch chain per block.
+    // An FP64 add / compare has a latency of ~40 cycles on sm_100a: every phase below is written as independent chains
+    // (register arrays filled first, compared afterwards), never as a load -> add -> compare -> branch chain per block.
     static_assert(TB <= 4 && BK == 4, "block minima are stored four rows wide; the scan takes two successor pairs per block");
     constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
+    constexpr int SB = 4;  // blocks per super-block of the coarse test
     const double inf = d_inf();
     long long tq = 0;
     if constexpr (PROF) tq = clock64();
 #define PH_LAP(k) do { if constexpr (PROF) { const long long tn = clock64(); ph[k] += tn - tq; tq = tn; } } while (0)
-    // ---- 1. block minima (lane = block; nblk is a multiple of 8, at most 32) and the seed block ---------------
-    unsigned int key = 0xffffffffu;
+    // ---- 1. block minima (lane = block; nblk is a multiple of 8, at most 32), super-block minima, one seed block per row
+    unsigned int key[TB];
+    double mall = inf;
+#pragma unroll
+    for (int r = 0; r < TB; ++r) key[r] = 0xffffffffu;
     if (lane < nblk) {
         double m[TB];
 #pragma unroll
@@ -337,66 +345,69 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
             const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK);
             const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK + 2);
             m[r] = fmin(fmin(w0.x, w0.y), fmin(w1.x, w1.y));
+            // seed of row r = a block with a (nearly) smallest minimum in that row: any block gives valid bounds, so a
+            // 27-bit order-preserving key of the minimum (rounded down to float) with the lane in the low bits is enough
+            const unsigned int u = __float_as_uint(__double2float_rd(m[r]));
+            key[r] = (((u & 0x80000000u) ? ~u : (u | 0x80000000u)) & ~31u) | (unsigned int)lane;
+            pm[4 * lane + r] = m[r];
+            mall = fmin(mall, m[r]);
         }
-        double mall = m[0];
-#pragma unroll
-        for (int r = 1; r < TB; ++r) mall = fmin(mall, m[r]);
-#pragma unroll
-        for (int r = 0; r < TB; ++r) pm[4 * lane + r] = m[r];
-        pmm[lane] = mall;
-        // seed = a block with a (nearly) smallest merged minimum: any block gives valid bounds, so a 27-bit order-
-        // preserving key of the minimum (rounded down to float) with the lane in the low bits is enough
-        const unsigned int u = __float_as_uint(__double2float_rd(mall));
-        key = (((u & 0x80000000u) ? ~u : (u | 0x80000000u)) & ~31u) | (unsigned int)lane;
     }
-    const int qs = (int)(__reduce_min_sync(0xffffffffu, key) & 31u);  // warp-uniform; also orders the pm / pmm writes
+    {   // super-block minima over all rows of the warp: the SB lanes of a super-block are neighbours
+        double ms = fmin(mall, __shfl_xor_sync(0xffffffffu, mall, 1));
+        ms = fmin(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
+        if (lane < nblk && (lane & (SB - 1)) == 0) pms[lane / SB] = ms;
+    }
+    int qs[TB];
+#pragma unroll
+    for (int r = 0; r < TB; ++r) qs[r] = min((int)(__reduce_min_sync(0xffffffffu, key[r]) & 31u), nblk - 1);  // warp-uniform
     __syncwarp();
     PH_LAP(0);
-    // ---- 2. upper bounds from the seed block (values only) ---------------------------------------------------
+    // ---- 2. upper bound of every cell's minimum: the smallest candidate of its row's seed block (values only) --------
     double ub[TB];
-    {
-        double a[BK];
 #pragma unroll
-        for (int jj = 0; jj < BK; ++jj) a[jj] = __dadd_rn(s, cs_l[(size_t)(qs * BK + jj) * Kp]);
-#pragma unroll
-        for (int r = 0; r < TB; ++r) {
-            const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs * BK);
-            const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs * BK + 2);
-            const double v0 = __dadd_rn(a[0], w0.x), v1 = __dadd_rn(a[1], w0.y), v2 = __dadd_rn(a[2], w1.x), v3 = __dadd_rn(a[3], w1.y);
-            double u01 = inf, u23 = inf;               // from +Inf with '>', so that a NaN candidate is ignored
-            if (u01 > v0) u01 = v0;
-            if (u23 > v2) u23 = v2;
-            if (u01 > v1) u01 = v1;
-            if (u23 > v3) u23 = v3;
-            ub[r] = u01 > u23 ? u23 : u01;
-            if (!live || r >= rows_live) ub[r] = -inf;  // pad levels and rows beyond the table never ask for a block
-        }
+    for (int r = 0; r < TB; ++r) {
+        const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs[r] * BK);
+        const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs[r] * BK + 2);
+        const double *cq = cs_l + (size_t)(qs[r] * BK) * Kp;
+        const double v0 = __dadd_rn(__dadd_rn(s, cq[0]), w0.x), v1 = __dadd_rn(__dadd_rn(s, cq[Kp]), w0.y);
+        const double v2 = __dadd_rn(__dadd_rn(s, cq[2 * Kp]), w1.x), v3 = __dadd_rn(__dadd_rn(s, cq[3 * Kp]), w1.y);
+        double u01 = inf, u23 = inf;               // from +Inf with '>', so that a NaN candidate is ignored
+        if (u01 > v0) u01 = v0;
+        if (u23 > v2) u23 = v2;
+        if (u01 > v1) u01 = v1;
+        if (u23 > v3) u23 = v3;
+        ub[r] = u01 > u23 ? u23 : u01;
+        // second bound: the candidate that stays on this lane's own level (no jump) -- with large jump costs the seed block
+        // of the row is far from most lanes' levels and bounds them badly (l_self is the lane's level, clamped to K - 1)
+        const double vself = __dadd_rn(__dadd_rn(s, cs_l[(size_t)l_self * Kp]), Prow[(size_t)r * Kp + l_self]);
+        if (ub[r] > vself) ub[r] = vself;
+        if (!live || r >= rows_live) ub[r] = -inf;  // pad levels and rows beyond the table never ask for a block
     }
     double ubmax = ub[0];
 #pragma unroll
     for (int r = 1; r < TB; ++r) ubmax = ub[r] > ubmax ? ub[r] : ubmax;
     PH_LAP(1);
     // ---- 3. which blocks can hold a minimum of some cell of this warp? --------------------------------------
-    unsigned int mneed = 0;
-#pragma unroll 1
-    for (int q0 = 0; q0 < nblk; q0 += 16) {  // cheap test, merged over the warp's rows: 16 independent chains per trip
-        double lb[16];
+    // coarse: super-blocks of SB blocks, bound merged over the warp's rows; exact per row on the blocks of the super-blocks
+    // that survive.  Both masks are OR-reduced over the warp: only a warp-uniform skip saves issue slots.
+    unsigned int sneed = 0;
+    {
+        double lbs[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int q = min(q0 + k, nblk - 1);
-            lb[k] = __dadd_rn(__dadd_rn(s, cm_l[(size_t)q * Kp]), pmm[q]);
+        for (int Q = 0; Q < 8; ++Q) {
+            const int Qc = min(Q, nblk / SB - 1);
+            lbs[Q] = __dadd_rn(__dadd_rn(s, cms_l[(size_t)Qc * Kp]), pms[Qc]);
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) mneed |= ((lb[k] > ubmax || q0 + k >= nblk) ? 0u : 1u) << ((q0 + k) & 31);
+        for (int Q = 0; Q < 8; ++Q) sneed |= ((lbs[Q] > ubmax || Q >= nblk / SB) ? 0u : 1u) << Q;
     }
-    const unsigned int m1 = __reduce_or_sync(0xffffffffu, mneed);
     unsigned int pneed = 0;
-#pragma unroll 1
-    for (int q0 = 0; q0 < nblk; q0 += 8) {  // exact test per row, eight blocks at a time, only where the cheap test said "maybe"
-        if (((m1 >> q0) & 0xffu) == 0u) continue;
-        double lbr[8][TB];
+    for (unsigned int ms = __reduce_or_sync(0xffffffffu, sneed); ms; ms &= ms - 1) {
+        const int q0 = (__ffs(ms) - 1) * SB;
+        double lbr[SB][TB];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < SB; ++k) {
             const double amin = __dadd_rn(s, cm_l[(size_t)(q0 + k) * Kp]);
             const double2 x = *reinterpret_cast<const double2 *>(pm + 4 * (q0 + k));
             const double2 y = *reinterpret_cast<const double2 *>(pm + 4 * (q0 + k) + 2);
@@ -405,14 +416,14 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
             for (int r = 0; r < TB; ++r) lbr[k][r] = __dadd_rn(amin, pmq[r]);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < SB; ++k) {
             bool nd = false;
 #pragma unroll
             for (int r = 0; r < TB; ++r) nd = nd || !(lbr[k][r] > ub[r]);
             pneed |= (nd ? 1u : 0u) << (q0 + k);
         }
     }
-    unsigned int m2 = __reduce_or_sync(0xffffffffu, pneed & m1);
+    unsigned int m2 = __reduce_or_sync(0xffffffffu, pneed);
     PH_LAP(2);
     // ---- 4. exhaustive scan of the surviving blocks, ascending, strict '>' -----------------------------------
     // The candidates of the NEXT surviving block are loaded and added while the compare -> move chain of the current
@@ -440,16 +451,17 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
         candidates(q, vc);
         for (;;) {
             double vn[TB][BK];
-            const int qn = m2 ? __ffs(m2) - 1 : -1;
+            const int qn = m2 ? __ffs(m2) - 1 : q;   // past the last block: a harmless reload instead of a branch
+            const bool more = m2 != 0;
             m2 &= m2 - 1;
-            if (qn >= 0) candidates(qn, vn);
+            candidates(qn, vn);
             executed += 1;
 #pragma unroll
             for (int jj = 0; jj < BK; ++jj)
 #pragma unroll
                 for (int r = 0; r < TB; ++r)
                     if (best[r][0] > vc[r][jj]) { BB_KEEP_BRANCH; best[r][0] = vc[r][jj]; arg[r][0] = q * BK + jj; }  // :73-76
-            if (qn < 0) break;
+            if (!more) break;
 #pragma unroll
             for (int r = 0; r < TB; ++r)
 #pragma unroll
@@ -625,7 +637,7 @@ __device__ __forceinline__ void scatter_tile(const FinishArgs &a, int row0, int 
 #pragma unroll
         for (int r = 0; r < TB; ++r) {
             const int row = row0 + r;
-            const bool in_tab = l < a.K && row < rows_left;
+            const bool in_tab = l < a.K && row < rows_left && row < a.R;  // (a ragged last row group reaches past the CTA's rows)
             const int x = row * a.Kp + l;
             const int y = x + bt * a.Kp;
             if (in_tab && a.r0 + row < bt) a.Pn[x] = inf;  // no source row: +Inf (:47)
@@ -1002,6 +1014,14 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             sm.cmin[x] = m;
         }
         __syncthreads();
+        for (int x = tid; x < (nblk / 4) * Kp; x += blockDim.x) {
+            const int Q = x / Kp, l = x - Q * Kp;
+            double m = inf;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m = fmin(m, sm.cmin[(size_t)(Q * 4 + k) * Kp + l]);
+            sm.cmins[x] = m;
+        }
+        __syncthreads();
     }
 
     if (tid >= NC + 64) {
@@ -1018,9 +1038,9 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     }
 
     // ========================================= COMPUTE warps ============================================
-    // Pruned scan (PR > 0): a lane is a level, a warp is a block of 32 levels x one of the two row groups (rows
-    // [0, TBA) and [TBA, TBA + TBB)); the warps of row group 1 follow those of group 0, so that every scheduler hosts
-    // one warp of each group.
+    // Pruned scan (PR > 0): a lane is a level, a warp is a block of 32 levels x a group of TBA consecutive rows (the
+    // last group may be ragged: the CTA owns TBB rows); the warps of a row group are consecutive, so that with four
+    // level blocks every scheduler hosts one warp of each group.
     const int nLB = Kp >> 5;
     const int pr_grp = PR > 0 ? (tid >> 5) / nLB : 0;
     const int pr_l = PR > 0 ? (((tid >> 5) % nLB) << 5) + (tid & 31) : 0;
@@ -1051,7 +1071,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             if (v == NV - 1) reds_release_inc(&sm.mbar[CNT_SCANNED]);
         }
     };
-    const int rowA = PR > 0 ? 0 : rg * TBA, rowB = PR > 0 ? TBA : c.RA + rg * TBB;
+    const int rowA = PR > 0 ? pr_grp * TBA : rg * TBA, rowB = PR > 0 ? 0 : c.RA + rg * TBB;
     unsigned int executed = 0;  // pruned scan: blocks this warp really scanned
     long long ph[4] = {0, 0, 0, 0};  // profile of the pruned scan: block minima + seed, upper bounds, masks, scan
     ArgT *pa = reinterpret_cast<ArgT *>(sm.pa);
@@ -1089,28 +1109,18 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             if constexpr (PR > 0) {
                 // ---- pruned scan: block minima of my rows, branch-and-bound scan, scatter from registers ----------
                 static_assert(TL == 1, "pruned scan: a lane is a level");
-                double *pm = sm.pmin + (size_t)(tid >> 5) * (c.Kr / PR) * 6;  // [nblk][4] row minima, then [nblk] merged (16-byte aligned)
-                double *pmm = pm + (size_t)(c.Kr / PR) * 4;
+                double *pm = sm.pmin + (size_t)(tid >> 5) * (c.Kr / PR) * 6;  // [nblk][4] row minima, then [nblk / 4] merged (16-byte aligned)
+                double *pms = pm + (size_t)(c.Kr / PR) * 4;
                 const FinishArgs fa = fin.stage_args(sl, i, T);
-                if (pr_grp == 0) {
-                    double best[TBA][1];
-                    int arg[TBA][1];
-                    scan_pruned<TBA, PR, ArgT, PROF>(Pc, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, t.B1 - fin.r0, lane, best, arg, executed, ph);
-                    PROF_LAP(1);
-                    scanned(0);  // the comm warp may refill the rows this stage read
-                    fin.wait_inputs(i, T);
-                    PROF_LAP(2);
-                    if (active) scatter_tile<TBA, 1, ArgT>(fa, 0, lg, best, arg);
-                } else if constexpr (TBB > 0) {
-                    double best[TBB][1];
-                    int arg[TBB][1];
-                    scan_pruned<TBB, PR, ArgT, PROF>(Pc + (size_t)TBA * Kp, sm.cs + lg, sm.cmin + lg, pm, pmm, ssc[lg], c.Kr / PR, Kp, active, t.B1 - fin.r0 - TBA, lane, best, arg, executed, ph);
-                    PROF_LAP(1);
-                    scanned(0);
-                    fin.wait_inputs(i, T);
-                    PROF_LAP(2);
-                    if (active) scatter_tile<TBB, 1, ArgT>(fa, TBA, lg, best, arg);
-                }
+                double best[TBA][1];
+                int arg[TBA][1];
+                scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cmin + lg, sm.cmins + lg, pm, pms, ssc[lg],
+                                                 c.Kr / PR, Kp, active, min(R, t.B1 - fin.r0) - rowA, lane, min(lg, K - 1), best, arg, executed, ph);
+                PROF_LAP(1);
+                scanned(0);  // the comm warp may refill the rows this stage read
+                fin.wait_inputs(i, T);
+                PROF_LAP(2);
+                if (active) scatter_tile<TBA, 1, ArgT>(fa, rowA, lg, best, arg);
                 finished();
                 PROF_LAP(3);
                 pc[4] += 1;
@@ -1165,7 +1175,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     if constexpr (PR > 0) {  // candidates really evaluated: blocks x successors x rows x live lanes of this warp
         if (c.exec && lane == 0) {
             const int live = min(32, max(0, K - (((tid >> 5) % nLB) << 5)));
-            atomicAdd(c.exec, (unsigned long long)executed * (unsigned long long)(PR * (pr_grp == 0 ? TBA : TBB) * live));
+            atomicAdd(c.exec, (unsigned long long)executed * (unsigned long long)(PR * max(0, min(TBA, R - rowA)) * live));
         }
     }
     if (PROF && c.prof && tid == 0 && self_finish) {
@@ -1196,15 +1206,16 @@ struct Variant { int TBA, TBB, TL, PR; };
 // (rows of sub-slice A, rows of sub-slice B, levels) per thread tile.  TBB = 0: one sub-slice; phase C then runs
 // after the scan, either on the compute warps themselves (NS = 0) or on scatter warps.  Every variant is built for
 // CTAs of up to 512 threads (128 registers per thread, no spills).
-// The last column is PR, the block size of the pruned scan (0 = exhaustive scan).  Pruned tiles: lane = level, the two
-// row groups (TBA and TBB rows) run side by side on different warps, the compute warps finish their own stage; built for
-// CTAs of up to 384 threads (8 compute warps + comm + publisher, 168 registers per thread).
+// The last column is PR, the block size of the pruned scan (0 = exhaustive scan).  Pruned tiles: lane = level, a warp is 32
+// levels x TBA consecutive rows, and the second column is the number of rows of the CTA (the last row group may be ragged:
+// 7 rows = 4 + 3 or 2 + 2 + 2 + 1); the row groups run side by side on different warps and the compute warps finish their
+// own stage.  Built for 4 * ceil(rows / TBA) compute warps + comm + publisher.
 #define BB200_VARIANTS(X)                                                                                      \
     X(0, 7, 0, 2, 0) X(1, 8, 0, 2, 0) X(2, 6, 0, 2, 0) X(3, 5, 0, 2, 0) X(4, 4, 0, 2, 0) X(5, 3, 0, 2, 0) X(6, 2, 0, 2, 0) X(7, 1, 0, 2, 0) \
     X(8, 8, 0, 1, 0) X(9, 4, 0, 1, 0) X(10, 2, 0, 1, 0) X(11, 1, 0, 1, 0)                                                    \
     X(12, 4, 3, 2, 0) X(13, 4, 4, 2, 0) X(14, 3, 3, 2, 0) X(15, 3, 2, 2, 0) X(16, 2, 2, 2, 0) X(17, 2, 1, 2, 0) X(18, 1, 1, 2, 0)     \
     X(19, 4, 4, 1, 0) X(20, 2, 2, 1, 0) X(21, 1, 1, 1, 0) X(22, 4, 3, 1, 0) X(23, 3, 3, 1, 0)                               \
-    X(24, 4, 3, 1, 4) X(25, 3, 2, 1, 4) X(26, 4, 4, 1, 4) X(27, 3, 3, 1, 4) X(28, 2, 2, 1, 4) X(29, 1, 1, 1, 4) X(30, 4, 0, 1, 4) X(31, 2, 0, 1, 4)
+    X(24, 4, 7, 1, 4) X(25, 2, 7, 1, 4) X(26, 4, 8, 1, 4) X(27, 2, 8, 1, 4) X(28, 2, 4, 1, 4) X(29, 1, 2, 1, 4) X(30, 4, 4, 1, 4) X(31, 3, 6, 1, 4)
 static const Variant kVariants[] = {
 #define X(idx, a, b, l, pr) {a, b, l, pr},
     BB200_VARIANTS(X)
@@ -1212,7 +1223,8 @@ static const Variant kVariants[] = {
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kWaveThreads = kWaveThreadsSmall;
-constexpr int kWaveThreadsPruned = 384;  // pruned tiles: up to 10 compute warps + comm + publisher, 168 registers per thread
+// pruned tiles: 4 level blocks x ceil(rows / TBA) row groups of compute warps + comm + publisher, rounded to 128 threads
+constexpr int pruned_max_threads(int tba, int rows) { return (32 * (4 * ((rows + tba - 1) / tba) + 2) + 127) / 128 * 128; }
 
 static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int NS, WaveCfg &c)
 {
@@ -1224,17 +1236,18 @@ static void fill_geometry(const Tables &t, int argw, int G, int JS, int v, int N
     const int tb = c.TB + c.TBB;
     const int rows_per_cta = (t.B1 + G - 1) / G;
     if (c.PR > 0) {
-        // pruned scan: the CTA owns exactly the tile's rows (RG = 1), one lane per level, one warp per 32 levels and
-        // row group; the caller rejects the variant when the slices do not fit (rows_per_cta > tb)
-        c.RG = 1;
-        c.R = tb;
-        c.RA = c.TB;
-        c.RB = c.TBB;
+        // pruned scan: the CTA owns TBB rows in ceil(TBB / TB) row groups of TB rows, one lane per level, one warp per 32
+        // levels and row group; the caller rejects the variant when the slices do not cover the table (G > SMs)
+        const int ng = (c.TBB + c.TB - 1) / c.TB;
+        c.RG = ng;
+        c.R = c.TBB;
+        c.RA = c.TBB;
+        c.RB = 0;
         c.G = (t.B1 + c.R - 1) / c.R;
         c.nLG = t.K;
         c.JS = 1;
         c.jper = c.Kr = (t.K + 8 * c.PR - 1) / (8 * c.PR) * (8 * c.PR);  // whole groups of eight blocks; rows K .. Kr-1 of the cost table are +Inf
-        c.tpg = t.Kp * (c.TBB > 0 ? 2 : 1);              // 32 lanes per level block and row group
+        c.tpg = t.Kp * ng;                               // 32 lanes per level block and row group
         c.NS = 0;
         c.EC = 2;
         c.NF = c.tpg / 32;
@@ -1272,6 +1285,8 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
 {
     if (t.M > kMaxM || argw != 1) return false;  // K > 255: the jump-cost table would not fit in shared memory anyway
     if ((long long)t.n >= ((long long)1 << 30)) return false;  // ticks are 32-bit; the host splits long batches into launches
+    const bool no_prune = want_variant < 0;  // -1: automatic choice among the exhaustive tiles only (the plan saw that pruning does not pay)
+    if (no_prune) want_variant = 0;
     const int want_ns = want_variant / 100;  // 0: automatic, 1..8: that many scatter warps, 10: none (NS = 0)
     want_variant %= 100;
     static const int kNsChoices[] = {0, 1, 2, 3, 4, 6, 8};
@@ -1283,7 +1298,7 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
         const int pr = kVariants[v].PR;
         if (pr > 0) {
             // the pruned scan pays when a stage has many successors to skip; narrow level sets keep the exhaustive tiles
-            if (want_variant == 0 && (!kAutoPruned || t.K < 64)) continue;
+            if (want_variant == 0 && (!kAutoPruned || no_prune || t.K < 64)) continue;
             if ((t.K + 8 * pr - 1) / (8 * pr) * (8 * pr) > t.Kp || (t.K + 8 * pr - 1) / (8 * pr) * 8 > 32) continue;  // whole groups of eight blocks, one mask word
         }
         for (int js = 1; js <= 16; ++js) {
@@ -1299,8 +1314,8 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 if (gmax > num_sms) gmax = num_sms;
                 WaveCfg c = cfg;
                 fill_geometry(t, argw, gmax, js, v, ns, c);
-                if (pr > 0 && (c.G > gmax || c.threads > kWaveThreadsPruned)) continue;  // the tile's rows x CTAs must cover the table
-                if (c.threads > kWaveThreads) continue;
+                if (pr > 0 && (c.G > gmax || c.threads > pruned_max_threads(kVariants[v].TBA, kVariants[v].TBB))) continue;  // rows x CTAs must cover the table
+                if (pr == 0 && c.threads > kWaveThreads) continue;
                 if (c.smem > smem_max) continue;
                 if ((size_t)c.JS * c.R * t.Kp >= ((size_t)1 << 30) || (size_t)t.B1 * t.Kp >= ((size_t)1 << 31) ||
                     c.R >= (1 << 15) || t.Kp >= (1 << 16))
@@ -1336,9 +1351,10 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     // per scheduler: the warps it hosts scan (TBA + TBB) rows x Kr successors between them; about half
                     // of the blocks are skipped on the BASELINE shapes (the skip rate is data dependent: it is measured,
                     // bb200_stats[17], not modelled); every block costs a bound check
+                    // fitted to profiles/phase_profile_r02_pruned.txt (config 4: 7 400 cycles per stage with two rows per warp)
                     const int nlb = t.Kp / 32, per_sched = (nlb + 3) / 4;
-                    const double full = 7.0 * (c.TB + c.TBB) * c.Kr * per_sched;
-                    stage = 0.5 * full + (c.Kr / pr) * 40.0 * per_sched * (c.TBB > 0 ? 2 : 1) + 600.0;
+                    const double full = 7.0 * c.R * c.Kr * per_sched;
+                    stage = 0.35 * full + 5000.0 + (c.TB > 2 ? 300.0 : 0.0);
                 } else if (c.TBB > 0) {
                     const double fa = finish(c.RA, true), fb = finish(c.RB, true);
                     // a shorter finish also shortens the lag a successor slice needs behind this one
@@ -1365,7 +1381,7 @@ template <int TBA, int TBB, int TL, int PR>
 static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStream_t st)
 {
     void *args[] = {(void *)&t, (void *)&cfg};
-    constexpr int MAXT = PR > 0 ? kWaveThreadsPruned : kWaveThreads;
+    constexpr int MAXT = PR > 0 ? pruned_max_threads(TBA, TBB) : kWaveThreads;
     // the cycle counters are a separate instantiation: their code would cost the production kernel ~1.5 %
     const void *fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR>
                               : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR>;

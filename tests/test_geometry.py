@@ -11,21 +11,29 @@ import pytest
 import mioc_b200 as m
 
 SMEM_MAX = 232448   # opt-in dynamic shared memory per CTA on sm_100 (227 KB)
-FIELDS = ("ok", "variant", "tba", "tbb", "tl", "ctas", "rows", "jsplit", "jper", "kr", "scatter_warps", "threads", "smem")
+FIELDS = ("ok", "variant", "tba", "tbb", "tl", "ctas", "rows", "jsplit", "jper", "kr", "scatter_warps", "threads", "smem",
+          "prune")
 
 
 def geometry(n, M, K, B, sms=148, smem=SMEM_MAX, ctas=0, jsplit=0, variant=0):
     lib = importlib.import_module(m.__name__ + "._lib").load()
-    out = np.zeros(13, dtype=np.int64)
+    out = np.zeros(14, dtype=np.int64)
     rc = lib.bb200_wave_geometry(n, M, K, B, sms, smem, ctas, jsplit, variant,
-                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 13)
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 14)
     assert rc == 0
     return dict(zip(FIELDS, out.tolist()))
 
 
 def test_config4_geometry_is_pinned():
+    # default: the pruned (branch-and-bound) scan -- lane = level, 2 rows per warp, 7 rows per CTA in 4 row groups,
+    # 4 level blocks x 4 row groups = 16 compute warps + comm + publisher, blocks of 4 successors
     g = geometry(100_000, 3, 125, 999)
-    assert g["ok"] == 1
+    assert g["ok"] == 1 and g["prune"] == 4
+    assert (g["tba"], g["tbb"], g["tl"]) == (2, 7, 1) and (g["ctas"], g["rows"]) == (143, 7)
+    assert (g["jsplit"], g["kr"], g["scatter_warps"], g["threads"]) == (1, 128, 0, 576) and g["smem"] <= SMEM_MAX
+    # variant -1 = what the plan falls back to when the bound test does not pay on its data: the exhaustive tiles
+    g = geometry(100_000, 3, 125, 999, variant=-1)
+    assert g["ok"] == 1 and g["prune"] == 0
     assert (g["tba"], g["tbb"], g["tl"]) == (4, 3, 2)          # two sub-slices of 4 + 3 rows, 2 levels per thread
     assert (g["ctas"], g["rows"]) == (143, 7)                  # 143 * 7 = 1001 >= B + 1 source rows on 148 SMs
     assert (g["jsplit"], g["jper"], g["kr"]) == (4, 32, 128)   # whole trips of the unrolled scan, +Inf pad rows 125..127
@@ -44,12 +52,15 @@ def test_geometry_invariants(K, B, n, sms):
     assert 1 <= g["ctas"] <= sms
     assert g["ctas"] * g["rows"] >= B + 1                      # every source row has an owner
     assert (g["ctas"] - 1) * g["rows"] < B + 1                 # and no CTA is empty
-    assert g["rows"] % (g["tba"] + g["tbb"]) == 0
-    assert g["threads"] % 32 == 0 and 96 <= g["threads"] <= 512
+    if g["prune"]:
+        assert g["rows"] == g["tbb"] and g["jsplit"] == 1 and g["scatter_warps"] == 0 and g["kr"] % 32 == 0
+    else:
+        assert g["rows"] % (g["tba"] + g["tbb"]) == 0
+    assert g["threads"] % 32 == 0 and 96 <= g["threads"] <= 640
     assert g["smem"] <= SMEM_MAX
     assert g["jsplit"] * g["jper"] >= K and g["jper"] % 2 == 0 # the j-groups cover every successor, in aligned pairs
     assert g["kr"] in (K, g["jsplit"] * g["jper"]) and g["kr"] <= max(K, Kp)
-    assert (g["tbb"] == 0) or g["scatter_warps"] >= 1          # two sub-slices need scatter warps
+    assert g["prune"] or (g["tbb"] == 0) or g["scatter_warps"] >= 1   # two sub-slices one after the other need scatter warps
 
 
 def test_shapes_the_wavefront_kernel_refuses():
