@@ -178,8 +178,8 @@ struct Smem {
     unsigned char *pa;  // ArgT[JS*R*Kp] partial argmins
     int *umap;        // [R*ceil(Kp/64)] phase-C work unit -> (row << 16) | first level
     double *cmin;     // pruned scan: [Kr/PR][Kp] block minima of the jump costs, cmin[q][l] = min_{j in block q} c_jl
-    double *pmin;     // pruned scan: [compute warps][6 * Kr/PR] block minima of the warp's value rows ([Kr/PR][4] per row, then the
-                      //              super-block minima merged over the rows, pad)
+    double *pmin;     // pruned scan: block minima of the CTA's value rows [8][Kr/PR], their super-block minima [8][8], the rows'
+                      //              seed blocks int[16], then 8 doubles of scratch per compute warp
     double *cmins;    // pruned scan: [Kr/PR/4][Kp] super-block (4 blocks) minima of the jump costs
 };
 
@@ -200,7 +200,7 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
                              (size_t)js_smem * c.R * t.Kp * (size_t)argw,
                              (size_t)c.R * (t.Kp / 32) * sizeof(int),
                              (size_t)nblk * t.Kp * sizeof(double),
-                             (size_t)(c.tpg / 32) * nblk * 6 * sizeof(double),
+                             c.PR ? (size_t)(8 * nblk + 64 + 8 + (c.tpg / 32) * 8) * sizeof(double) : 0,
                              (size_t)(nblk / 4) * t.Kp * sizeof(double)};
     for (int k = 0; k < 11; ++k) {
         o[k] = off;
@@ -302,132 +302,139 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
     }
 }
 
-// Pruned scan of one thread: TB rows x ONE level (lane = level), successors in blocks of BK (at most 32 blocks).
-//   Prow: the warp's value rows [r][Kp];  cs_l = cs + l: jump costs c[j][l] at stride Kp;  cm_l = cmin + l: their block
-//   minima at stride Kp;  pm / pmm: this warp's scratch for the block minima of its value rows;  s: stage cost of l.
-// Two passes, so that no decision depends on the order of the scan (no compare -> vote -> branch chain per block):
-//   1. block minima of the warp's rows, pm[q][r] = min_{j in block q} P[r][j] and pmm[q] = min_r pm[q][r] (NaN ignored: a
-//      NaN candidate never wins; pad columns may hold anything, they only lower a bound);
-//   2. an upper bound UB[r] of every cell's minimum: the smallest candidate of ONE seed block (the block with the
-//      smallest pmm -- any block gives a valid bound, this one a good one);
-//   3. LB[q][r] = (s + cmin[q][l]) + pm[q][r] is a lower bound of every candidate of block q in the same floating-point
+// ---- pruned scan ------------------------------------------------------------------------------------------
+// Block minima of ONE value row, computed once per stage and row by one warp for all the warps that scan the row
+// (lane = block of BK successors; nblk is a multiple of 8, at most 32):
+//   pmr[q] = min_{j in block q} P[j]  (NaN ignored: a NaN candidate never wins; pad columns may hold anything finite or
+//   +Inf, they only lower a bound),  pmsr[Q] = minimum of super-block Q (4 blocks),  *qseed = a block with a (nearly)
+//   smallest minimum -- any block gives valid bounds, so a 27-bit order-preserving key of the minimum (rounded down to
+//   float) with the lane in the low bits and one REDUX.MIN are enough.
+template <int BK>
+__device__ __forceinline__ void row_minima(const double *__restrict__ Prow, double *__restrict__ pmr, double *__restrict__ pmsr,
+                                           int *__restrict__ qseed, int nblk, int lane)
+{
+    static_assert(BK == 4, "two successor pairs per block");
+    double m = d_inf();
+    unsigned int key = 0xffffffffu;
+    if (lane < nblk) {
+        const double2 w0 = *reinterpret_cast<const double2 *>(Prow + lane * BK);
+        const double2 w1 = *reinterpret_cast<const double2 *>(Prow + lane * BK + 2);
+        m = fmin(fmin(w0.x, w0.y), fmin(w1.x, w1.y));
+        pmr[lane] = m;
+        const unsigned int u = __float_as_uint(__double2float_rd(m));
+        key = (((u & 0x80000000u) ? ~u : (u | 0x80000000u)) & ~31u) | (unsigned int)lane;
+    }
+    double ms = fmin(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    ms = fmin(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
+    if (lane < nblk && (lane & 3) == 0) pmsr[lane >> 2] = ms;
+    const unsigned int kmin = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0) *qseed = min((int)(kmin & 31u), nblk - 1);
+}
+
+// Pruned scan of one thread: TB rows x ONE level (lane = level), successors in blocks of BK.
+//   Prow: the warp's value rows [r][Kp];  cs_l = cs + l: jump costs c[j][l] at stride Kp;  cm_l / cms_l: their block /
+//   super-block minima at stride Kp;  pmr / pmsr / qseed: the rows' minima and seeds (row_minima), row strides nblk / 8 / 1;
+//   pmw: 8 doubles of scratch of this warp;  s: stage cost of this level.
+//   1. UB[r]: an upper bound of every cell's minimum -- the smallest candidate of its row's seed block and the no-jump
+//      candidate j = l (with large jump costs the seed block is far from most lanes' levels and bounds them badly);
+//   2. LB[q][r] = (s + cmin[q][l]) + pm[q][r] is a lower bound of every candidate of block q in the SAME floating-point
 //      arithmetic (rounded addition is monotone in both operands).  If LB > UB for every cell of the warp, no candidate
-//      of the block can be a minimum or tie with one, so the block is dropped; first with a cheap test merged over the
-//      warp's rows ((s + cmin) + pmm against max_r UB), then exactly on the blocks that survive it.  The masks are
-//      OR-reduced over the warp: only a warp-uniform skip saves issue slots;
-//   4. the surviving blocks are scanned in ascending order with the reference's strict '>' from +Inf: the same minimum,
+//      of the block can be a minimum or tie with one, and the block is dropped: first per super-block with a bound
+//      merged over the warp's rows, then exactly per row on the blocks of the super-blocks that survive.  Both masks are
+//      OR-reduced over the warp (only a warp-uniform skip saves issue slots);
+//   3. the surviving blocks are scanned in ascending order with the reference's strict '>' from +Inf: the same minimum,
 //      the same (earliest) argmin, bit for bit.
+// An FP64 add / compare has a latency of ~40 cycles on sm_100a: every phase is written as independent chains (register
+// arrays first, compares afterwards); in the scan only ONE compare -> move step per block sits on the chain through `best`
+// (the block's own minimum is a small tournament that does not depend on it), and the next block's candidates are loaded
+// and added while the current tournament runs.
 template <int TB, int BK, typename ArgT, bool PROF>
 __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
                                             const double *__restrict__ cm_l, const double *__restrict__ cms_l,
-                                            double *__restrict__ pm, double *__restrict__ pms, double s, int nblk, int Kp,
-                                            bool live, int rows_live, int lane, int l_self, double (&best)[TB][1],
+                                            const double *__restrict__ pmr, const double *__restrict__ pmsr,
+                                            const int *__restrict__ qseed, double *__restrict__ pmw, double s, int nblk,
+                                            int Kp, bool live, int rows_live, int lane, int l_self, double (&best)[TB][1],
                                             int (&arg)[TB][1], unsigned int &executed, long long (&ph)[4])
 {
-    // An FP64 add / compare has a latency of ~40 cycles on sm_100a: every phase below is written as independent chains
-    // (register arrays filled first, compared afterwards), never as a load -> add -> compare -> branch chain per block.
-    static_assert(TB <= 4 && BK == 4, "block minima are stored four rows wide; the scan takes two successor pairs per block");
+    static_assert(TB <= 4 && BK == 4, "the scan takes two successor pairs per block");
     constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
     constexpr int SB = 4;  // blocks per super-block of the coarse test
     const double inf = d_inf();
     long long tq = 0;
     if constexpr (PROF) tq = clock64();
 #define PH_LAP(k) do { if constexpr (PROF) { const long long tn = clock64(); ph[k] += tn - tq; tq = tn; } } while (0)
-    // ---- 1. block minima (lane = block; nblk is a multiple of 8, at most 32), super-block minima, one seed block per row
-    unsigned int key[TB];
-    double mall = inf;
+    // super-block minima merged over this warp's rows (lane Q < 8 computes, everybody reads)
+    if (lane < 8) {
+        double m = pmsr[lane];
 #pragma unroll
-    for (int r = 0; r < TB; ++r) key[r] = 0xffffffffu;
-    if (lane < nblk) {
-        double m[TB];
-#pragma unroll
-        for (int r = 0; r < TB; ++r) {
-            const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK);
-            const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + lane * BK + 2);
-            m[r] = fmin(fmin(w0.x, w0.y), fmin(w1.x, w1.y));
-            // seed of row r = a block with a (nearly) smallest minimum in that row: any block gives valid bounds, so a
-            // 27-bit order-preserving key of the minimum (rounded down to float) with the lane in the low bits is enough
-            const unsigned int u = __float_as_uint(__double2float_rd(m[r]));
-            key[r] = (((u & 0x80000000u) ? ~u : (u | 0x80000000u)) & ~31u) | (unsigned int)lane;
-            pm[4 * lane + r] = m[r];
-            mall = fmin(mall, m[r]);
-        }
+        for (int r = 1; r < TB; ++r) m = fmin(m, pmsr[r * 8 + lane]);
+        pmw[lane] = m;
     }
-    {   // super-block minima over all rows of the warp: the SB lanes of a super-block are neighbours
-        double ms = fmin(mall, __shfl_xor_sync(0xffffffffu, mall, 1));
-        ms = fmin(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
-        if (lane < nblk && (lane & (SB - 1)) == 0) pms[lane / SB] = ms;
-    }
-    int qs[TB];
-#pragma unroll
-    for (int r = 0; r < TB; ++r) qs[r] = min((int)(__reduce_min_sync(0xffffffffu, key[r]) & 31u), nblk - 1);  // warp-uniform
     __syncwarp();
     PH_LAP(0);
-    // ---- 2. upper bound of every cell's minimum: the smallest candidate of its row's seed block (values only) --------
+    // ---- 1. upper bounds ---------------------------------------------------------------------------------
     double ub[TB];
 #pragma unroll
     for (int r = 0; r < TB; ++r) {
-        const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs[r] * BK);
-        const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + qs[r] * BK + 2);
-        const double *cq = cs_l + (size_t)(qs[r] * BK) * Kp;
+        const int q = qseed[r];
+        const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + q * BK);
+        const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + q * BK + 2);
+        const double *cq = cs_l + (size_t)(q * BK) * Kp;
         const double v0 = __dadd_rn(__dadd_rn(s, cq[0]), w0.x), v1 = __dadd_rn(__dadd_rn(s, cq[Kp]), w0.y);
         const double v2 = __dadd_rn(__dadd_rn(s, cq[2 * Kp]), w1.x), v3 = __dadd_rn(__dadd_rn(s, cq[3 * Kp]), w1.y);
+        const double vself = __dadd_rn(__dadd_rn(s, cs_l[(size_t)l_self * Kp]), Prow[(size_t)r * Kp + l_self]);
         double u01 = inf, u23 = inf;               // from +Inf with '>', so that a NaN candidate is ignored
         if (u01 > v0) u01 = v0;
         if (u23 > v2) u23 = v2;
         if (u01 > v1) u01 = v1;
         if (u23 > v3) u23 = v3;
+        if (u01 > vself) u01 = vself;
         ub[r] = u01 > u23 ? u23 : u01;
-        // second bound: the candidate that stays on this lane's own level (no jump) -- with large jump costs the seed block
-        // of the row is far from most lanes' levels and bounds them badly (l_self is the lane's level, clamped to K - 1)
-        const double vself = __dadd_rn(__dadd_rn(s, cs_l[(size_t)l_self * Kp]), Prow[(size_t)r * Kp + l_self]);
-        if (ub[r] > vself) ub[r] = vself;
         if (!live || r >= rows_live) ub[r] = -inf;  // pad levels and rows beyond the table never ask for a block
     }
     double ubmax = ub[0];
 #pragma unroll
     for (int r = 1; r < TB; ++r) ubmax = ub[r] > ubmax ? ub[r] : ubmax;
     PH_LAP(1);
-    // ---- 3. which blocks can hold a minimum of some cell of this warp? --------------------------------------
-    // coarse: super-blocks of SB blocks, bound merged over the warp's rows; exact per row on the blocks of the super-blocks
-    // that survive.  Both masks are OR-reduced over the warp: only a warp-uniform skip saves issue slots.
+    // ---- 2. which blocks can hold a minimum of some cell of this warp? --------------------------------------
     unsigned int sneed = 0;
     {
+        const double2 p01 = *reinterpret_cast<const double2 *>(pmw), p23 = *reinterpret_cast<const double2 *>(pmw + 2);
+        const double2 p45 = *reinterpret_cast<const double2 *>(pmw + 4), p67 = *reinterpret_cast<const double2 *>(pmw + 6);
+        const double pq[8] = {p01.x, p01.y, p23.x, p23.y, p45.x, p45.y, p67.x, p67.y};
         double lbs[8];
 #pragma unroll
-        for (int Q = 0; Q < 8; ++Q) {
-            const int Qc = min(Q, nblk / SB - 1);
-            lbs[Q] = __dadd_rn(__dadd_rn(s, cms_l[(size_t)Qc * Kp]), pms[Qc]);
-        }
+        for (int Q = 0; Q < 8; ++Q) lbs[Q] = __dadd_rn(__dadd_rn(s, cms_l[(size_t)min(Q, nblk / SB - 1) * Kp]), pq[Q]);
 #pragma unroll
         for (int Q = 0; Q < 8; ++Q) sneed |= ((lbs[Q] > ubmax || Q >= nblk / SB) ? 0u : 1u) << Q;
     }
     unsigned int pneed = 0;
-    for (unsigned int ms = __reduce_or_sync(0xffffffffu, sneed); ms; ms &= ms - 1) {
-        const int q0 = (__ffs(ms) - 1) * SB;
-        double lbr[SB][TB];
+    for (unsigned int ms = __reduce_or_sync(0xffffffffu, sneed); ms;) {
+        // two surviving super-blocks per trip (the second may repeat the first): 8 independent exact tests
+        const int qa = (__ffs(ms) - 1) * SB;
+        ms &= ms - 1;
+        const int qb = ms ? (__ffs(ms) - 1) * SB : qa;
+        ms &= ms - 1;
+        double lbr[2 * SB][TB];
 #pragma unroll
-        for (int k = 0; k < SB; ++k) {
-            const double amin = __dadd_rn(s, cm_l[(size_t)(q0 + k) * Kp]);
-            const double2 x = *reinterpret_cast<const double2 *>(pm + 4 * (q0 + k));
-            const double2 y = *reinterpret_cast<const double2 *>(pm + 4 * (q0 + k) + 2);
-            const double pmq[4] = {x.x, x.y, y.x, y.y};
+        for (int k = 0; k < 2 * SB; ++k) {
+            const int q = (k < SB ? qa : qb) + (k & (SB - 1));
+            const double amin = __dadd_rn(s, cm_l[(size_t)q * Kp]);
 #pragma unroll
-            for (int r = 0; r < TB; ++r) lbr[k][r] = __dadd_rn(amin, pmq[r]);
+            for (int r = 0; r < TB; ++r) lbr[k][r] = __dadd_rn(amin, pmr[r * nblk + q]);
         }
 #pragma unroll
-        for (int k = 0; k < SB; ++k) {
+        for (int k = 0; k < 2 * SB; ++k) {
+            const int q = (k < SB ? qa : qb) + (k & (SB - 1));
             bool nd = false;
 #pragma unroll
             for (int r = 0; r < TB; ++r) nd = nd || !(lbr[k][r] > ub[r]);
-            pneed |= (nd ? 1u : 0u) << (q0 + k);
+            pneed |= (nd ? 1u : 0u) << q;
         }
     }
     unsigned int m2 = __reduce_or_sync(0xffffffffu, pneed);
     PH_LAP(2);
-    // ---- 4. exhaustive scan of the surviving blocks, ascending, strict '>' -----------------------------------
-    // The candidates of the NEXT surviving block are loaded and added while the compare -> move chain of the current
-    // one runs (the chain through `best` is the only true dependency between blocks).
+    // ---- 3. exhaustive scan of the surviving blocks, ascending, strict '>' -----------------------------------
 #pragma unroll
     for (int r = 0; r < TB; ++r) { best[r][0] = inf; arg[r][0] = MARKI; }
     auto candidates = [&](int q, double (&v)[TB][BK]) {
@@ -444,23 +451,39 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
             v[r][3] = __dadd_rn(a[3], w1.y);
         }
     };
+    // the minimum of one block, earliest successor on ties, NaN ignored -- exactly what the sequential scan of the block
+    // from +Inf would leave: two sequential pairs from +Inf, then the later pair only wins with a strictly smaller value
+    auto block_min = [&](const double (&v)[TB][BK], int q, double (&mv)[TB], int (&ma)[TB]) {
+#pragma unroll
+        for (int r = 0; r < TB; ++r) {
+            double m01 = inf, m23 = inf;
+            int a01 = MARKI, a23 = MARKI;
+            if (m01 > v[r][0]) { BB_KEEP_BRANCH; m01 = v[r][0]; a01 = q * BK; }
+            if (m23 > v[r][2]) { BB_KEEP_BRANCH; m23 = v[r][2]; a23 = q * BK + 2; }
+            if (m01 > v[r][1]) { BB_KEEP_BRANCH; m01 = v[r][1]; a01 = q * BK + 1; }
+            if (m23 > v[r][3]) { BB_KEEP_BRANCH; m23 = v[r][3]; a23 = q * BK + 3; }
+            if (m01 > m23) { BB_KEEP_BRANCH; m01 = m23; a01 = a23; }
+            mv[r] = m01;
+            ma[r] = a01;
+        }
+    };
     if (m2) {
         double vc[TB][BK];
         int q = __ffs(m2) - 1;
         m2 &= m2 - 1;
         candidates(q, vc);
         for (;;) {
-            double vn[TB][BK];
-            const int qn = m2 ? __ffs(m2) - 1 : q;   // past the last block: a harmless reload instead of a branch
+            double vn[TB][BK], mv[TB];
+            int ma[TB];
             const bool more = m2 != 0;
+            const int qn = more ? __ffs(m2) - 1 : q;   // past the last block: a harmless reload instead of a branch
             m2 &= m2 - 1;
             candidates(qn, vn);
+            block_min(vc, q, mv, ma);
             executed += 1;
 #pragma unroll
-            for (int jj = 0; jj < BK; ++jj)
-#pragma unroll
-                for (int r = 0; r < TB; ++r)
-                    if (best[r][0] > vc[r][jj]) { BB_KEEP_BRANCH; best[r][0] = vc[r][jj]; arg[r][0] = q * BK + jj; }  // :73-76
+            for (int r = 0; r < TB; ++r)
+                if (best[r][0] > mv[r]) { BB_KEEP_BRANCH; best[r][0] = mv[r]; arg[r][0] = ma[r]; }   // :73-76 across blocks
             if (!more) break;
 #pragma unroll
             for (int r = 0; r < TB; ++r)
@@ -1014,6 +1037,8 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             sm.cmin[x] = m;
         }
         __syncthreads();
+        for (int x = tid; x < 8 * nblk + 64; x += blockDim.x) sm.pmin[x] = inf;  // rows the CTA does not own bound nothing
+        if (tid < 16) reinterpret_cast<int *>(sm.pmin + 8 * nblk + 64)[tid] = 0;
         for (int x = tid; x < (nblk / 4) * Kp; x += blockDim.x) {
             const int Q = x / Kp, l = x - Q * Kp;
             double m = inf;
@@ -1109,13 +1134,20 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             if constexpr (PR > 0) {
                 // ---- pruned scan: block minima of my rows, branch-and-bound scan, scatter from registers ----------
                 static_assert(TL == 1, "pruned scan: a lane is a level");
-                double *pm = sm.pmin + (size_t)(tid >> 5) * (c.Kr / PR) * 6;  // [nblk][4] row minima, then [nblk / 4] merged (16-byte aligned)
-                double *pms = pm + (size_t)(c.Kr / PR) * 4;
+                const int nblk = c.Kr / PR;
+                double *pmR = sm.pmin, *pmsR = sm.pmin + 8 * nblk;
+                int *qseed = reinterpret_cast<int *>(sm.pmin + 8 * nblk + 64);
+                double *pmw = sm.pmin + 8 * nblk + 72 + (tid >> 5) * 8;
+                // block minima and seed of every row, once per stage: warp w takes the rows w, w + warps, ...
+                for (int r = tid >> 5; r < R; r += NC >> 5)
+                    row_minima<PR>(Pc + (size_t)r * Kp, pmR + r * nblk, pmsR + r * 8, qseed + r, nblk, lane);
+                asm volatile("bar.sync 1, %0;" ::"r"(NC) : "memory");
                 const FinishArgs fa = fin.stage_args(sl, i, T);
                 double best[TBA][1];
                 int arg[TBA][1];
-                scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cmin + lg, sm.cmins + lg, pm, pms, ssc[lg],
-                                                 c.Kr / PR, Kp, active, min(R, t.B1 - fin.r0) - rowA, lane, min(lg, K - 1), best, arg, executed, ph);
+                scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cmin + lg, sm.cmins + lg, pmR + rowA * nblk,
+                                                 pmsR + rowA * 8, qseed + rowA, pmw, ssc[lg], nblk, Kp, active,
+                                                 min(R, t.B1 - fin.r0) - rowA, lane, min(lg, K - 1), best, arg, executed, ph);
                 PROF_LAP(1);
                 scanned(0);  // the comm warp may refill the rows this stage read
                 fin.wait_inputs(i, T);
