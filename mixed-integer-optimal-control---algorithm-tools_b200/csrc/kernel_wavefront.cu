@@ -83,6 +83,18 @@ __device__ __forceinline__ void sts_release(uint64_t *p, unsigned long long v)
     asm volatile("st.release.cta.shared::cta.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
 }
 // 32-bit event counters: native shared-memory RED; compared wrap-safe (difference as signed)
+// One hand-over = ONE release fence, then relaxed signals: an arrive with release semantics and a release RED are two
+// fences, and a CTA-scope fence waits for the warp's outstanding global stores (~400 cycles each after the argmin /
+// ring stores of a stage).  fence + relaxed write is a release pattern of the PTX memory model.
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void reds_relaxed_inc(uint64_t *p)
+{
+    asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(1u) : "memory");
+}
 __device__ __forceinline__ void reds_release_inc(uint64_t *p)
 {
     asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(1u) : "memory");
@@ -345,9 +357,8 @@ __device__ __forceinline__ void row_minima(const double *__restrict__ Prow, doub
 //   3. the surviving blocks are scanned in ascending order with the reference's strict '>' from +Inf: the same minimum,
 //      the same (earliest) argmin, bit for bit.
 // An FP64 add / compare has a latency of ~40 cycles on sm_100a: every phase is written as independent chains (register
-// arrays first, compares afterwards); in the scan only ONE compare -> move step per block sits on the chain through `best`
-// (the block's own minimum is a small tournament that does not depend on it), and the next block's candidates are loaded
-// and added while the current tournament runs.
+// arrays first, compares afterwards); in the scan the next block's candidates are loaded and added while the compare ->
+// move chain of the current block runs.
 template <int TB, int BK, typename ArgT, bool PROF>
 __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
                                             const double *__restrict__ cm_l, const double *__restrict__ cms_l,
@@ -451,45 +462,31 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
             v[r][3] = __dadd_rn(a[3], w1.y);
         }
     };
-    // the minimum of one block, earliest successor on ties, NaN ignored -- exactly what the sequential scan of the block
-    // from +Inf would leave: two sequential pairs from +Inf, then the later pair only wins with a strictly smaller value
-    auto block_min = [&](const double (&v)[TB][BK], int q, double (&mv)[TB], int (&ma)[TB]) {
+    auto relax = [&](const double (&v)[TB][BK], int q) {
 #pragma unroll
-        for (int r = 0; r < TB; ++r) {
-            double m01 = inf, m23 = inf;
-            int a01 = MARKI, a23 = MARKI;
-            if (m01 > v[r][0]) { BB_KEEP_BRANCH; m01 = v[r][0]; a01 = q * BK; }
-            if (m23 > v[r][2]) { BB_KEEP_BRANCH; m23 = v[r][2]; a23 = q * BK + 2; }
-            if (m01 > v[r][1]) { BB_KEEP_BRANCH; m01 = v[r][1]; a01 = q * BK + 1; }
-            if (m23 > v[r][3]) { BB_KEEP_BRANCH; m23 = v[r][3]; a23 = q * BK + 3; }
-            if (m01 > m23) { BB_KEEP_BRANCH; m01 = m23; a01 = a23; }
-            mv[r] = m01;
-            ma[r] = a01;
-        }
+        for (int jj = 0; jj < BK; ++jj)
+#pragma unroll
+            for (int r = 0; r < TB; ++r)
+                if (best[r][0] > v[r][jj]) { BB_KEEP_BRANCH; best[r][0] = v[r][jj]; arg[r][0] = q * BK + jj; }  // :73-76
     };
+    // (a per-block tournament that keeps only one compare -> move step on the chain through `best` was measured: 50 % more
+    // moves, and with four warps per scheduler the chain latency is hidden anyway -- slower)
     if (m2) {
-        double vc[TB][BK];
-        int q = __ffs(m2) - 1;
+        double va[TB][BK], vb[TB][BK];   // two blocks in flight, alternating roles: no register copies between trips
+        int qa = __ffs(m2) - 1, qb = 0;
         m2 &= m2 - 1;
-        candidates(q, vc);
+        candidates(qa, va);
         for (;;) {
-            double vn[TB][BK], mv[TB];
-            int ma[TB];
-            const bool more = m2 != 0;
-            const int qn = more ? __ffs(m2) - 1 : q;   // past the last block: a harmless reload instead of a branch
-            m2 &= m2 - 1;
-            candidates(qn, vn);
-            block_min(vc, q, mv, ma);
+            if (m2) { qb = __ffs(m2) - 1; candidates(qb, vb); }
+            relax(va, qa);
             executed += 1;
-#pragma unroll
-            for (int r = 0; r < TB; ++r)
-                if (best[r][0] > mv[r]) { BB_KEEP_BRANCH; best[r][0] = mv[r]; arg[r][0] = ma[r]; }   // :73-76 across blocks
-            if (!more) break;
-#pragma unroll
-            for (int r = 0; r < TB; ++r)
-#pragma unroll
-                for (int jj = 0; jj < BK; ++jj) vc[r][jj] = vn[r][jj];
-            q = qn;
+            if (!m2) break;
+            m2 &= m2 - 1;
+            if (m2) { qa = __ffs(m2) - 1; candidates(qa, va); }
+            relax(vb, qb);
+            executed += 1;
+            if (!m2) break;
+            m2 &= m2 - 1;
         }
     }
     PH_LAP(3);
@@ -527,16 +524,15 @@ struct FinishArgs {
     int JS, R, Kp, K, B1, r0;
 };
 
-// Finishes the work units [ub, ue) of a sub-slice; warp sw of NS takes every NS-th one.  A unit is 32 * EC
-// consecutive levels of one source row: a lane owns EC neighbouring cells and fetches their partial minima with
-// 16-byte loads (EC / 2 per j-group) and all EC argmins with one load.  Phase C is latency bound, so what counts is
-// the number of units a warp has to walk through one after the other: EC = 4 (a whole 128-level row per unit) when
-// that gives every scatter warp at most one unit of a sub-slice, EC = 2 otherwise.
+// Finishes the work units [ub, ue) of a sub-slice; warp sw of NS takes every NS-th one.  A unit is 64 consecutive
+// levels of one source row: a lane owns EC = 2 neighbouring cells and fetches their partial minima with one 16-byte load
+// per j-group and both argmins with one 2-byte load.  (Four cells per lane -- a whole 128-level row per unit -- shortened
+// the finishing pass but its larger code slowed the scan by more, profiles/README.md; the variant was removed.)
 template <int JSC, int EC, typename ArgT, bool PROF>
 __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue, int sw, int NS, int lane, long long *pcc)
 {
     static_assert(sizeof(ArgT) == 1, "the packed argmin load assumes one byte per cell");
-    static_assert(EC == 2 || EC == 4, "two or four cells per lane");
+    static_assert(EC == 2, "two cells per lane");
     long long tq0 = 0;
     if constexpr (PROF) tq0 = pcc ? clock64() : 0;
     const double inf = d_inf();
@@ -556,14 +552,8 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
         const int l0 = min((m & 0xffff) + EC * lane, a.Kp - EC);  // a partly filled last unit re-reads the last cells
         const bool lane_live = (m & 0xffff) + EC * lane < a.Kp;
         const int x = row * a.Kp + l0;
-        int bt[EC];
-        if constexpr (EC == 4) {
-            const int4 b4 = *reinterpret_cast<const int4 *>(btp + l0);
-            bt[0] = b4.x; bt[1] = b4.y; bt[2] = b4.z; bt[3] = b4.w;
-        } else {
-            const int2 b2 = *reinterpret_cast<const int2 *>(btp + l0);
-            bt[0] = b2.x; bt[1] = b2.y;
-        }
+        const int2 b2 = *reinterpret_cast<const int2 *>(btp + l0);
+        const int bt[EC] = {b2.x, b2.y};
         double val[EC];
         int arg[EC], y[EC];
         bool no_src[EC], ok[EC];
@@ -584,8 +574,7 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
                 v[2 * h] = w.x;
                 v[2 * h + 1] = w.y;
             }
-            if constexpr (EC == 4) g = *reinterpret_cast<const unsigned int *>(pa + q * RK + x);
-            else g = (unsigned int)*reinterpret_cast<const unsigned short *>(pa + q * RK + x);
+            g = (unsigned int)*reinterpret_cast<const unsigned short *>(pa + q * RK + x);
         };
         unsigned int gsel[EC];  // the packed argmins of the group that currently wins cell e
         if constexpr (JSC > 0) {
@@ -630,7 +619,10 @@ __device__ __forceinline__ void finish_rows(const FinishArgs &a, int ub, int ue,
 #pragma unroll
         for (int e = 0; e < EC; ++e) {
             if (no_src[e]) Pn[x + e] = inf;
-            if (ok[e]) __stcs(argrow + x + e, (unsigned char)arg[e]);  // written once, streamed: do not displace the ring in L2
+            // written once, streamed (do not displace the ring in L2).  EVERY byte of an owned row is written -- pad levels
+            // and cells outside `for b = 0:B-b~` get MARK -- so that no 32-byte sector of the table is written partially
+            // (a partial sector costs a DRAM read-modify-write: 3.6 GB of reads per launch at config 4)
+            if (lane_live && row < rows_left) __stcs(argrow + x + e, ok[e] ? (unsigned char)arg[e] : (unsigned char)0xff);
             if (ok[e] && y[e] < RK) Pn[y[e]] = val[e];
             if (ok[e] && y[e] >= RK) hring[y[e]] = val[e];
         }
@@ -664,8 +656,11 @@ __device__ __forceinline__ void scatter_tile(const FinishArgs &a, int row0, int 
             const int x = row * a.Kp + l;
             const int y = x + bt * a.Kp;
             if (in_tab && a.r0 + row < bt) a.Pn[x] = inf;  // no source row: +Inf (:47)
-            if (in_tab && row + bt < rows_left) {           // inside `for b = 0:B-b~` (:69)
-                __stcs(argrow + x, (ArgT)arg[r][q]);  // written once, streamed: do not displace the ring in L2
+            const bool okc = in_tab && row + bt < rows_left;  // inside `for b = 0:B-b~` (:69)
+            // argmin: written once, streamed; every byte of an owned row is written (MARK in pad levels and out-of-range
+            // cells) so that no 32-byte sector is written partially (see finish_rows)
+            if (row < rows_left && row < a.R && l < a.Kp) __stcs(argrow + x, okc ? (ArgT)arg[r][q] : (ArgT) ~(ArgT)0);
+            if (okc) {
                 if (y < RK) a.Pn[y] = best[r][q];
                 else a.hring[y] = best[r][q];
                 if (a.phi) a.phi[y] = best[r][q];
@@ -759,8 +754,6 @@ struct Finisher {
     __device__ __forceinline__ void rows(const FinishArgs &a, int ub, int ue)
     {
         long long *pccp = (PROF && c.prof) ? pcc : nullptr;
-        // EC = 4 (a whole 128-level row per unit, one unit per scatter warp) was measured too: the finishing pass of
-        // sub-slice A gets shorter (3 500 -> 2 400 cycles) but its larger code slows the scan by more (profiles/README.md)
         switch (c.JS) {
             case 2: finish_rows<2, 2, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
             case 4: finish_rows<4, 2, ArgT, PROF>(a, ub, ue, fw, NF, lane, pccp); break;
@@ -789,8 +782,9 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
     auto finished = [&](int v) {
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&sm.mbar[MB_FINISHED + v]);
-            if (v == NV - 1) reds_release_inc(&sm.mbar[CNT_FINISHED]);
+            fence_cta();
+            mbar_arrive_relaxed(&sm.mbar[MB_FINISHED + v]);
+            if (v == NV - 1) reds_relaxed_inc(&sm.mbar[CNT_FINISHED]);
         }
     };
 
@@ -1092,8 +1086,9 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     auto scanned = [&](int v) {
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&sm.mbar[MB_SCANNED + v]);
-            if (v == NV - 1) reds_release_inc(&sm.mbar[CNT_SCANNED]);
+            fence_cta();
+            mbar_arrive_relaxed(&sm.mbar[MB_SCANNED + v]);
+            if (v == NV - 1) reds_relaxed_inc(&sm.mbar[CNT_SCANNED]);
         }
     };
     const int rowA = PR > 0 ? pr_grp * TBA : rg * TBA, rowB = PR > 0 ? 0 : c.RA + rg * TBB;
@@ -1110,8 +1105,9 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     auto finished = [&]() {
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&sm.mbar[MB_FINISHED]);
-            reds_release_inc(&sm.mbar[CNT_FINISHED]);
+            fence_cta();
+            mbar_arrive_relaxed(&sm.mbar[MB_FINISHED]);
+            reds_relaxed_inc(&sm.mbar[CNT_FINISHED]);
         }
     };
 
@@ -1138,10 +1134,11 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 double *pmR = sm.pmin, *pmsR = sm.pmin + 8 * nblk;
                 int *qseed = reinterpret_cast<int *>(sm.pmin + 8 * nblk + 64);
                 double *pmw = sm.pmin + 8 * nblk + 72 + (tid >> 5) * 8;
-                // block minima and seed of every row, once per stage: warp w takes the rows w, w + warps, ...
-                for (int r = tid >> 5; r < R; r += NC >> 5)
+                // block minima and seed of the rows of my row group, once per stage: the group's warps (one per level block)
+                // share its rows, then meet at the group's own named barrier (not a CTA-wide one)
+                for (int r = rowA + (tid >> 5) % nLB; r < min(rowA + TBA, R); r += nLB)
                     row_minima<PR>(Pc + (size_t)r * Kp, pmR + r * nblk, pmsR + r * 8, qseed + r, nblk, lane);
-                asm volatile("bar.sync 1, %0;" ::"r"(NC) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + pr_grp), "r"(32 * nLB) : "memory");
                 const FinishArgs fa = fin.stage_args(sl, i, T);
                 double best[TBA][1];
                 int arg[TBA][1];
@@ -1152,7 +1149,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
                 scanned(0);  // the comm warp may refill the rows this stage read
                 fin.wait_inputs(i, T);
                 PROF_LAP(2);
-                if (active) scatter_tile<TBA, 1, ArgT>(fa, rowA, lg, best, arg);
+                scatter_tile<TBA, 1, ArgT>(fa, rowA, lg, best, arg);  // pad levels only write their MARK bytes
                 finished();
                 PROF_LAP(3);
                 pc[4] += 1;
@@ -1237,7 +1234,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 struct Variant { int TBA, TBB, TL, PR; };
 // (rows of sub-slice A, rows of sub-slice B, levels) per thread tile.  TBB = 0: one sub-slice; phase C then runs
 // after the scan, either on the compute warps themselves (NS = 0) or on scatter warps.  Every variant is built for
-// CTAs of up to 512 threads (128 registers per thread, no spills).
+// CTAs of up to 512 threads (128 registers per thread; the largest tiles spill a little and are penalised by the model).
 // The last column is PR, the block size of the pruned scan (0 = exhaustive scan).  Pruned tiles: lane = level, a warp is 32
 // levels x TBA consecutive rows, and the second column is the number of rows of the CTA (the last row group may be ragged:
 // 7 rows = 4 + 3 or 2 + 2 + 2 + 1); the row groups run side by side on different warps and the compute warps finish their
@@ -1375,7 +1372,7 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                     const int units = rows * ((t.Kp + 32 * c.EC - 1) / (32 * c.EC));
                     const int per_warp = (units + c.NF - 1) / c.NF;
                     const double generic = (js == 2 || js == 4) ? 1.0 : 1.5;  // other splits: rolled combine loop
-                    return per_warp * generic * (c.EC == 4 ? 1.4 : 1.0) * (hidden ? 1200.0 + 50.0 * js : 100.0 + 310.0 * js) + 300.0;
+                    return per_warp * generic * (hidden ? 1200.0 + 50.0 * js : 100.0 + 310.0 * js) + 300.0;
                 };
                 const double sa = scan(c.TB), sb = scan(c.TBB);
                 double stage;
@@ -1398,6 +1395,13 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                         stage = sa + finish(c.RA, false) + 600.0;  // + the hand-over after the scan
                 }
                 stage += 10.0 * c.NS;  // scatter warps take issue slots from the scan
+                // tiles ptxas cannot keep in 128 registers (-Xptxas -v: 8x2 596 B, 6x2 104 B, 8x1 40 B, 7x2 24 B of spills)
+                // pay for their local-memory traffic inside the scan loop
+                if (pr == 0) {
+                    const int cells = (c.TB > c.TBB ? c.TB : c.TBB) * c.TL;
+                    if (cells >= 16) stage *= 1.5;
+                    else if (cells >= 12 || (c.TB == 8 && c.TL == 1)) stage *= 1.15;
+                }
                 if (!found || stage < best_stage) {
                     best_stage = stage;
                     cfg = c;
