@@ -235,7 +235,8 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *  17 candidates the last DP really evaluated when it ran the pruned scan (else 0): the exhaustive count is
  *     bb200_count_updates; the difference was skipped by the bound test, results are bit-identical
  *  18 block size of the pruned scan of the current geometry (0: exhaustive scan)
- *  19 1 if the plan went back to the exhaustive tiles because the bound test skipped < 40 % on its data
+ *  19 1 if the plan went back to the exhaustive tiles because its DP evaluated more candidates than the measured
+ *     break-even of the pruned scan (13 %): a data / horizon dependent choice, results are identical either way
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);
 

@@ -93,6 +93,7 @@ struct bb200_plan {
     cudaEvent_t ev_prep = nullptr, ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_batch[2] = {nullptr, nullptr};
     double *h_in[2] = {nullptr, nullptr}, *h_out[2] = {nullptr, nullptr}, *h_recs[2] = {nullptr, nullptr};
     int *h_errs[2] = {nullptr, nullptr};
+    unsigned long long *h_execs[2] = {nullptr, nullptr};
     size_t h_in_elems = 0, h_out_elems = 0;
     double last_batch_ms = 0., batch_syncs = 0., batch_waves = 0.;
     // pinned staging
@@ -231,6 +232,7 @@ void destroy_plan(bb200_plan *p)
         if (p->h_out[k]) cudaFreeHost(p->h_out[k]);
         if (p->h_recs[k]) cudaFreeHost(p->h_recs[k]);
         if (p->h_errs[k]) cudaFreeHost(p->h_errs[k]);
+        if (p->h_execs[k]) cudaFreeHost(p->h_execs[k]);
         if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
         if (p->ev_out[k]) cudaEventDestroy(p->ev_out[k]);
         if (p->ev_batch[k]) cudaEventDestroy(p->ev_batch[k]);
@@ -385,13 +387,16 @@ bool ensure_graph(bb200_plan *p)
 }
 
 // The pruned scan only pays when its bound test drops most blocks; that depends on the data (jump costs against the
-// spread of the value rows).  After a synchronised DP: if more than 60 % of the candidates were evaluated anyway, this
-// plan goes back to the exhaustive tiles for its following DPs (TRM calls the DP again and again on similar data).
-void adapt_pruning(bb200_plan *p, int slots)
+// spread of the value rows, and the horizon: the first stages after the terminal one bound little).  Measured break-even
+// on B200 against the exhaustive tiles: 13 % of the candidates evaluated (config 4 at n = 20 000; n = 100 000 evaluates
+// 7.7 % and is 1.26x faster, n = 10 000 evaluates 17 % and is 7 % slower).  After a synchronised DP that evaluated more,
+// the plan goes back to the exhaustive tiles for its following DPs (TRM / a batch call the DP again on similar data).
+constexpr double kPruneBreakEven = 0.13;
+void adapt_pruning(bb200_plan *p, int slots, unsigned long long executed)
 {
     if (!p->wave_ok || p->cfg.PR == 0 || p->tune_variant != 0 || p->prune_off) return;
     const double full = (double)(p->n > 1 ? p->n - 1 : 1) * p->B1 * (double)p->cfg.Kr * p->K * slots;
-    if ((double)*p->h_exec > 0.6 * full) {
+    if ((double)executed > kPruneBreakEven * full) {
         p->prune_off = true;
         p->prune_switches += 1;
         if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }  // geometry is baked in
@@ -405,7 +410,7 @@ int sync_and_check(bb200_plan *p)
     CU(cudaMemcpyAsync(p->h_err, p->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(p->h_exec, p->d_exec, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
-    if (p->dp_timed) adapt_pruning(p, p->last_dp_slots);
+    if (p->dp_timed) adapt_pruning(p, p->last_dp_slots, *p->h_exec);
     if (p->dp_timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->last_dp_ms = ms;
@@ -732,7 +737,7 @@ int bb200_solve(bb200_plan *plan, const double *df, const double *u_old, int64_t
         plan->launches += 4 + (one_launch ? 0 : (double)plan->n - 1);  // prep, DP, selection, backtrack
         plan->last_path = plan->mini_ok ? 2 : (plan->wave_ok ? 1 : 0);
         plan->graph_replays += 1;
-        adapt_pruning(plan, 1);
+        adapt_pruning(plan, 1, *plan->h_exec);
         std::memcpy(u_out, plan->h_u, io);
         if (phi_star) *phi_star = plan->h_rec[0];
         if (b_star) *b_star = (int64_t)plan->h_rec[1];
@@ -766,6 +771,7 @@ static int ensure_batch_pipe(bb200_plan *p, int n_radii, bool want_u)
             CU(cudaEventCreate(&p->ev_batch[k]));
             CU(cudaMallocHost((void **)&p->h_recs[k], (size_t)p->batch * kRecDoubles * sizeof(double)));
             CU(cudaMallocHost((void **)&p->h_errs[k], 4 * sizeof(int)));
+            CU(cudaMallocHost((void **)&p->h_execs[k], sizeof(unsigned long long)));
         }
     }
     const size_t in_need = (size_t)p->batch * 2 * io;
@@ -856,6 +862,7 @@ int bb200_solve_batched_shard(bb200_plan *plan, int64_t S, int64_t first, int64_
         const double *hr = plan->h_recs[w & 1];
         const int *he = plan->h_errs[w & 1];
         if (he[2]) return fail(BB200_ERR_CUDA, "wavefront kernel watchdog fired: a pipeline dependency was never satisfied");
+        adapt_pruning(plan, cnt, *plan->h_execs[w & 1]);  // later waves run on the exhaustive tiles if pruning did not pay
         for (int s = 0; s < cnt; ++s) {
             const int64_t gs = sub(w, s);
             const bool inexact = hr[(size_t)s * kRecDoubles + 4 * kMaxRadii] != 0.;
@@ -899,6 +906,7 @@ int bb200_solve_batched_shard(bb200_plan *plan, int64_t S, int64_t first, int64_
             CU(cudaMemcpyAsync(plan->h_out[w & 1], plan->d_usweep, (size_t)cnt * n_radii * io * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(plan->h_recs[w & 1], plan->d_rec_all, (size_t)cnt * kRecDoubles * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(plan->h_errs[w & 1], plan->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(plan->h_execs[w & 1], plan->d_exec, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(plan->ev_out[w & 1], st));
         if (w + 1 == waves) CU(cudaEventRecord(plan->ev_batch[1], st));
         if (w > 0 && (rc = drain(w - 1))) return rc;
