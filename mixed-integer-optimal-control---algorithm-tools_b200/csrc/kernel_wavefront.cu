@@ -107,6 +107,13 @@ __device__ __forceinline__ unsigned int lds_acquire_u32(const uint64_t *p)
 }
 // has the counter reached `want` events?  (events are counted modulo 2^32; the lag is always far below 2^31)
 __device__ __forceinline__ bool reached(unsigned int cnt, unsigned int want) { return (int)(cnt - want) >= 0; }
+// Has EVERY warp counted by the `groups` counters at `word` (warps_per_group each) signalled `events` events?
+__device__ __forceinline__ bool all_reached(const uint64_t *word, int groups, unsigned int warps_per_group, unsigned int events)
+{
+    bool ok = true;
+    for (int g = 0; g < groups; ++g) ok = ok && reached(lds_acquire_u32(word + g), events * warps_per_group);
+    return ok;
+}
 
 // mbarrier wait with a watchdog: a lost hand-over becomes an error code (err[2] watchdog, err[3] abort) instead of
 // a hung GPU.  Once the abort flag is up every wait gives up quickly so that the launch drains.  The waiting loop is
@@ -164,6 +171,40 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, int
 #else
 #define BB_KEEP_BRANCH
 #endif
+// Value-row buffers in shared memory.  With THREE buffers the halo rows of stage i-1 may land while stage i is still being
+// scanned (the buffer they go to was last read by stage i+2), so the TMA round trip is off the critical path; with two
+// buffers it sits between the scan and the scatter of every stage.
+#ifndef BB_PS_BUFS
+#define BB_PS_BUFS 3
+#endif
+// Pruned tiles: hand a stage over with ONE named barrier of the compute warps + the publisher warp instead of
+// fence.acq_rel.cta + mbarrier arrive/wait per warp: the CTA-scope fence waits for the warp's outstanding argmin / ring
+// stores (L2 round trip) on the critical path of every stage.  The publisher's fence.acq_rel.gpu after the barrier is
+// cumulative over everything the barrier ordered (the pattern of a cooperative-groups grid sync).
+#ifndef BB_BAR_HANDOVER
+#define BB_BAR_HANDOVER 0
+#endif
+// Pruned tiles: the row groups of a CTA hand their stages over group by group instead of meeting at one CTA-wide barrier.
+// Budget only flows upwards, so the rows of group k for stage i-1 are complete as soon as the groups 0 .. k have scattered
+// stage i; a group that is done early starts its next stage at once and the groups drift out of phase, which lets the
+// schedulers overlap the latency-bound phases of one group (block minima, upper bounds, bound tests) with the issue-bound
+// scan of another.  Requires two value-row buffers (the halo TMA of stage i is issued after EVERY warp has scanned stage
+// i+1, which keeps the groups less than one stage apart) and the mbarrier hand-over.
+#ifndef BB_GROUP_PIPE
+#define BB_GROUP_PIPE 0
+#endif
+#if BB_GROUP_PIPE
+#undef BB_PS_BUFS
+#define BB_PS_BUFS 2
+#undef BB_BAR_HANDOVER
+#define BB_BAR_HANDOVER 0
+#endif
+#ifndef BB_KPC
+#define BB_KPC 1   // 0: never launch the instantiations with a compile-time level count (A/B builds)
+#endif
+constexpr int kMaxRowGroups = 4;   // row groups of a pruned tile (wave_configure rejects more)
+constexpr int kPsBufs = BB_PS_BUFS;
+constexpr int kStageBarrier = 8;   // named barrier id of the stage hand-over (ids 1..7: the row groups of the pruned scan)
 constexpr int kUnrollB = BB_UNROLL;  // successor pairs per trip of the phase-B loop
 constexpr bool kAutoPruned = true;  // may the geometry model pick pruned tiles by itself (wide level sets only)?
 constexpr int kNever = 0x7fffffff;  // "no bound": ticks are 32-bit, wave_configure refuses launches with >= 2^30 steps
@@ -171,28 +212,34 @@ constexpr int kNever = 0x7fffffff;  // "no bound": ticks are 32-bit, wave_config
 // shared-memory synchronisation words
 enum {
     MB_COST = 0,      // [0..2]  cost rows of global step T landed in buffer T % 3           (TMA, tx count)
-    MB_HALO = 3,      // [3..4]  halo rows pushed during stage i landed, barrier i & 1        (TMA, tx count)
-    MB_SCANNED = 5,   // [5..6]  compute warps finished phase B of sub-slice v                (one arrival per warp)
-    MB_FINISHED = 7,  // [7..8]  scatter warps finished phase C of sub-slice v                (one arrival per warp)
-    CNT_SCANNED = 9,  // counter: compute-warp arrivals after the LAST sub-slice of a stage
-    CNT_FINISHED = 10,  // counter: scatter-warp arrivals after the LAST sub-slice of a step (terminal stage included)
-    RING_OK = 11,     // counter: highest global step whose pushes may overwrite their ring slot
-    SYNC_WORDS = 16
+    MB_HALO = 3,      // [3..5]  halo rows pushed during stage i landed, barrier i % 3        (TMA, tx count)
+    MB_SCANNED = 6,   // [6..7]  compute warps finished phase B of sub-slice v                (one arrival per warp)
+    MB_FINISHED = 8,  // [8..9]  scatter warps finished phase C of sub-slice v                (one arrival per warp)
+    CNT_SCANNED = 10,  // counter: compute-warp arrivals after the LAST sub-slice of a stage
+    CNT_FINISHED = 11,  // counter: scatter-warp arrivals after the LAST sub-slice of a step (terminal stage included)
+    RING_OK = 12,     // counter: highest global step whose pushes may overwrite their ring slot
+    MB_GFIN = 13,     // [13..20] pruned tiles, group pipeline: row group k scattered stage i, barrier 13 + 2 k + (i & 1)  (one
+                      //          arrival per warp of the group; two alternating barriers per group: a waiter may find its
+                      //          barrier one completion ahead, never two, and parity waits alias at two)
+    CNT_GSCANNED = 21,  // [21..24] group pipeline: the counters above PER ROW GROUP.  A sum over groups that are up to a stage
+    CNT_GFINISHED = 25, // [25..28] apart cannot tell "every warp has done step T"; inside a group the warps are at most one
+                        //          step apart, where the sum can
+    SYNC_WORDS = 32
 };
 
 struct Smem {
     uint64_t *mbar;   // SYNC_WORDS synchronisation words, see the enum above
     double *ss;       // [3][Kp]   stage cost of global step T in ss[T%3]        (TMA destination)
     int *bts;         // [3][Kp]   budget use of global step T in bts[T%3]       (TMA destination)
-    double *Ps;       // [2][R][Kp] value rows (row-major) read by stage i in Ps[i&1]  (halo rows: TMA destination)
+    double *Ps;       // [kPsBufs][R][Kp] value rows (row-major) read by stage i in Ps[i % kPsBufs]  (halo rows: TMA destination)
     double *cs;       // [K*Kp]    jump costs
     double *pv;       // [JS*R*Kp] partial minima of the j-groups
     unsigned char *pa;  // ArgT[JS*R*Kp] partial argmins
     int *umap;        // [R*ceil(Kp/64)] phase-C work unit -> (row << 16) | first level
-    double *cmin;     // pruned scan: [Kr/PR][Kp] block minima of the jump costs, cmin[q][l] = min_{j in block q} c_jl
-    double *pmin;     // pruned scan: block minima of the CTA's value rows [8][Kr/PR], their super-block minima [8][8], the rows'
-                      //              seed blocks int[16], then 8 doubles of scratch per compute warp
-    double *cmins;    // pruned scan: [Kr/PR/4][Kp] super-block (4 blocks) minima of the jump costs
+    float *cminf;     // pruned scan: [Kr/PR][Kp] block minima of the jump costs ROUNDED DOWN to float,
+                      //              cminf[q][l] <= min_{j in block q} c_jl
+    float *pminf;     // pruned scan: block minima of the CTA's value rows rounded down to float [8][Kr/PR], then the rows' seed
+                      //              blocks int[16]
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -200,21 +247,20 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int argw, unsigned char *base, Smem *s)
 {
     size_t off = 0;
-    size_t o[11];
+    size_t o[10];
     const int nblk = c.PR ? c.Kr / c.PR : 0;
     const int js_smem = c.PR ? 0 : c.JS;  // pruned tiles keep no partial minima in shared memory
-    const size_t sizes[11] = {SYNC_WORDS * sizeof(uint64_t),
+    const size_t sizes[10] = {SYNC_WORDS * sizeof(uint64_t),
                              3 * (size_t)t.Kp * sizeof(double),
                              3 * (size_t)t.Kp * sizeof(int),
-                             2 * (size_t)t.Kp * c.R * sizeof(double),
+                             kPsBufs * (size_t)t.Kp * c.R * sizeof(double),
                              (size_t)c.Kr * t.Kp * sizeof(double),
                              (size_t)js_smem * c.R * t.Kp * sizeof(double),
                              (size_t)js_smem * c.R * t.Kp * (size_t)argw,
                              (size_t)c.R * (t.Kp / 32) * sizeof(int),
-                             (size_t)nblk * t.Kp * sizeof(double),
-                             c.PR ? (size_t)(8 * nblk + 64 + 8 + (c.tpg / 32) * 8) * sizeof(double) : 0,
-                             (size_t)(nblk / 4) * t.Kp * sizeof(double)};
-    for (int k = 0; k < 11; ++k) {
+                             (size_t)nblk * t.Kp * sizeof(float),
+                             c.PR ? (size_t)(8 * nblk + 16) * sizeof(float) : 0};
+    for (int k = 0; k < 10; ++k) {
         o[k] = off;
         off = align_up(off + sizes[k], 128);
     }
@@ -227,9 +273,8 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
         s->pv = reinterpret_cast<double *>(base + o[5]);
         s->pa = base + o[6];
         s->umap = reinterpret_cast<int *>(base + o[7]);
-        s->cmin = reinterpret_cast<double *>(base + o[8]);
-        s->pmin = reinterpret_cast<double *>(base + o[9]);
-        s->cmins = reinterpret_cast<double *>(base + o[10]);
+        s->cminf = reinterpret_cast<float *>(base + o[8]);
+        s->pminf = reinterpret_cast<float *>(base + o[9]);
     }
     return off;
 }
@@ -315,137 +360,136 @@ __device__ __forceinline__ void scan_tile(const double *__restrict__ Prow, const
 }
 
 // ---- pruned scan ------------------------------------------------------------------------------------------
+// The bound tests run in FP32 with DIRECTED rounding; only the surviving candidates are evaluated in FP64.  Why that is
+// rigorous: a candidate is v = fl64(fl64(s + c_jl) + P[j]) (HelpFunctions.jl:67, :71).  With sf <= s, cf <= c_jl, pf <= P[j]
+// (floats, rounded down) the float chain rd32(rd32(sf + cf) + pf) is a double that is <= the exact sum of its operands
+// at every step, and fl64 is monotone and leaves doubles unchanged -- hence LB32 <= v, for every candidate of the block
+// whose minima cf, pf are.  An upper bound UB of the cell's minimum is rounded UP to float.  LB32 > UBf therefore proves
+// v > UB: the candidate can neither be the minimum nor tie with it.  No error analysis is involved in this test.
+//
+// order-preserving map float -> uint32 (for REDUX.MIN/MAX, which only take integers) and back
+__device__ __forceinline__ unsigned int f2key(float x)
+{
+    const unsigned int u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned int k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
 // Block minima of ONE value row, computed once per stage and row by one warp for all the warps that scan the row
 // (lane = block of BK successors; nblk is a multiple of 8, at most 32):
-//   pmr[q] = min_{j in block q} P[j]  (NaN ignored: a NaN candidate never wins; pad columns may hold anything finite or
-//   +Inf, they only lower a bound),  pmsr[Q] = minimum of super-block Q (4 blocks),  *qseed = a block with a (nearly)
-//   smallest minimum -- any block gives valid bounds, so a 27-bit order-preserving key of the minimum (rounded down to
-//   float) with the lane in the low bits and one REDUX.MIN are enough.
+//   pmr[q] = rd32(min_{j in block q} P[j])  (NaN ignored: a NaN candidate never wins; pad columns may hold anything finite
+//   or +Inf, they only lower a bound),  *jseed = a successor with a (nearly) smallest value -- any successor gives a valid
+//   upper bound, so a 27-bit key of the block minimum with the lane in the low bits and one REDUX.MIN are enough.
 template <int BK>
-__device__ __forceinline__ void row_minima(const double *__restrict__ Prow, double *__restrict__ pmr, double *__restrict__ pmsr,
-                                           int *__restrict__ qseed, int nblk, int lane)
+__device__ __forceinline__ void row_minima(const double *__restrict__ Prow, float *__restrict__ pmr, int *__restrict__ jseed, int nblk,
+                                           int lane)
 {
     static_assert(BK == 4, "two successor pairs per block");
-    double m = d_inf();
     unsigned int key = 0xffffffffu;
+    int jmin = 0;
     if (lane < nblk) {
         const double2 w0 = *reinterpret_cast<const double2 *>(Prow + lane * BK);
         const double2 w1 = *reinterpret_cast<const double2 *>(Prow + lane * BK + 2);
-        m = fmin(fmin(w0.x, w0.y), fmin(w1.x, w1.y));
-        pmr[lane] = m;
-        const unsigned int u = __float_as_uint(__double2float_rd(m));
-        key = (((u & 0x80000000u) ? ~u : (u | 0x80000000u)) & ~31u) | (unsigned int)lane;
+        const double m01 = fmin(w0.x, w0.y), m23 = fmin(w1.x, w1.y), m = fmin(m01, m23);
+        jmin = (m == m01) ? (m == w0.x ? 0 : 1) : (m == w1.x ? 2 : 3);   // (all NaN: any successor will do)
+        const float mf = __double2float_rd(m);
+        pmr[lane] = mf;
+        key = (f2key(mf) & ~31u) | (unsigned int)lane;
     }
-    double ms = fmin(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    ms = fmin(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
-    if (lane < nblk && (lane & 3) == 0) pmsr[lane >> 2] = ms;
     const unsigned int kmin = __reduce_min_sync(0xffffffffu, key);
-    if (lane == 0) *qseed = min((int)(kmin & 31u), nblk - 1);
+    if (lane == (int)(kmin & 31u) && lane < nblk) *jseed = lane * BK + jmin;   // the lane that holds the smallest key
 }
 
 // Pruned scan of one thread: TB rows x ONE level (lane = level), successors in blocks of BK.
-//   Prow: the warp's value rows [r][Kp];  cs_l = cs + l: jump costs c[j][l] at stride Kp;  cm_l / cms_l: their block /
-//   super-block minima at stride Kp;  pmr / pmsr / qseed: the rows' minima and seeds (row_minima), row strides nblk / 8 / 1;
-//   pmw: 8 doubles of scratch of this warp;  s: stage cost of this level.
-//   1. UB[r]: an upper bound of every cell's minimum -- the smallest candidate of its row's seed block and the no-jump
-//      candidate j = l (with large jump costs the seed block is far from most lanes' levels and bounds them badly);
-//   2. LB[q][r] = (s + cmin[q][l]) + pm[q][r] is a lower bound of every candidate of block q in the SAME floating-point
-//      arithmetic (rounded addition is monotone in both operands).  If LB > UB for every cell of the warp, no candidate
-//      of the block can be a minimum or tie with one, and the block is dropped: first per super-block with a bound
-//      merged over the warp's rows, then exactly per row on the blocks of the super-blocks that survive.  Both masks are
-//      OR-reduced over the warp (only a warp-uniform skip saves issue slots);
-//   3. the surviving blocks are scanned in ascending order with the reference's strict '>' from +Inf: the same minimum,
+//   Prow: the warp's value rows [r][Kp];  cs_l = cs + l: jump costs c[j][l] at stride Kp;  cmf_l: their block minima (float,
+//   rounded down) at stride Kp;  pmf / qseed: the rows' block minima (float, rounded down) and seeds (row_minima), row
+//   strides nblk / 1;  s: stage cost of this level;  cw: (lane = block q) the smallest cmf[q][l] over the live levels of
+//   this warp;  cmx: the largest finite jump cost into this level (for the slack below).
+//   1. UB[r]: an upper bound of every cell's minimum -- the candidate of its row's seed successor (a smallest value of the
+//      row) and the no-jump candidate j = l, evaluated exactly (FP64).  (The other candidates of the seed's block tighten
+//      the bound by < 5 % of the surviving blocks, tools/prune_stats.py, and cost more than that.);
+//   2. row test, lane = block: block q of row r can matter to SOME level of this warp only if
+//          cw[q] + pm[q][r]  <=  max_l (UB[r][l] - s_l)
+//      -- one compare per (block, row) for the whole warp instead of one per (block, row, level).  The merge over the
+//      levels is an argument in real arithmetic, so both sides carry a slack of 2^-30 of the magnitudes involved, which
+//      covers the two fl64 roundings of a candidate (2^-52 relative) a million times over;
+//   3. level test, lane = level, on the blocks that survive 2.:  LB32[q][r] = rd32(rd32(sf + cmf[q][l]) + pmf[q][r]) > UBf[r]
+//      (the monotone chain of the header comment).  The masks are OR-reduced over the warp: only a warp-uniform skip
+//      saves issue slots;
+//   4. the surviving blocks are scanned in ascending order with the reference's strict '>' from +Inf: the same minimum,
 //      the same (earliest) argmin, bit for bit.
-// An FP64 add / compare has a latency of ~40 cycles on sm_100a: every phase is written as independent chains (register
-// arrays first, compares afterwards); in the scan the next block's candidates are loaded and added while the compare ->
-// move chain of the current block runs.
+// FP64 adds / compares have ~40 cycles of latency on sm_100a: phases 1 and 4 are written as independent chains, and in the
+// scan the next block's candidates are loaded and added while the compare -> move chain of the current block runs.
 template <int TB, int BK, typename ArgT, bool PROF>
 __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
-                                            const double *__restrict__ cm_l, const double *__restrict__ cms_l,
-                                            const double *__restrict__ pmr, const double *__restrict__ pmsr,
-                                            const int *__restrict__ qseed, double *__restrict__ pmw, double s, int nblk,
+                                            const float *__restrict__ cmf_l, const float *__restrict__ pmf,
+                                            const int *__restrict__ qseed, double s, float cw, float cmx, int nblk,
                                             int Kp, bool live, int rows_live, int lane, int l_self, double (&best)[TB][1],
                                             int (&arg)[TB][1], unsigned int &executed, long long (&ph)[4])
 {
     static_assert(TB <= 4 && BK == 4, "the scan takes two successor pairs per block");
     constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
-    constexpr int SB = 4;  // blocks per super-block of the coarse test
     const double inf = d_inf();
+    const float finf = __int_as_float(0x7f800000), fmax = __int_as_float(0x7f7fffff);
     long long tq = 0;
     if constexpr (PROF) tq = clock64();
 #define PH_LAP(k) do { if constexpr (PROF) { const long long tn = clock64(); ph[k] += tn - tq; tq = tn; } } while (0)
-    // super-block minima merged over this warp's rows (lane Q < 8 computes, everybody reads)
-    if (lane < 8) {
-        double m = pmsr[lane];
-#pragma unroll
-        for (int r = 1; r < TB; ++r) m = fmin(m, pmsr[r * 8 + lane]);
-        pmw[lane] = m;
-    }
-    __syncwarp();
     PH_LAP(0);
     // ---- 1. upper bounds ---------------------------------------------------------------------------------
     double ub[TB];
+    const double cself = cs_l[(size_t)l_self * Kp];
 #pragma unroll
     for (int r = 0; r < TB; ++r) {
-        const int q = qseed[r];
-        const double2 w0 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + q * BK);
-        const double2 w1 = *reinterpret_cast<const double2 *>(Prow + (size_t)r * Kp + q * BK + 2);
-        const double *cq = cs_l + (size_t)(q * BK) * Kp;
-        const double v0 = __dadd_rn(__dadd_rn(s, cq[0]), w0.x), v1 = __dadd_rn(__dadd_rn(s, cq[Kp]), w0.y);
-        const double v2 = __dadd_rn(__dadd_rn(s, cq[2 * Kp]), w1.x), v3 = __dadd_rn(__dadd_rn(s, cq[3 * Kp]), w1.y);
-        const double vself = __dadd_rn(__dadd_rn(s, cs_l[(size_t)l_self * Kp]), Prow[(size_t)r * Kp + l_self]);
-        double u01 = inf, u23 = inf;               // from +Inf with '>', so that a NaN candidate is ignored
-        if (u01 > v0) u01 = v0;
-        if (u23 > v2) u23 = v2;
-        if (u01 > v1) u01 = v1;
-        if (u23 > v3) u23 = v3;
-        if (u01 > vself) u01 = vself;
-        ub[r] = u01 > u23 ? u23 : u01;
+        const int js = qseed[r];
+        const double vseed = __dadd_rn(__dadd_rn(s, cs_l[(size_t)js * Kp]), Prow[(size_t)r * Kp + js]);
+        const double vself = __dadd_rn(__dadd_rn(s, cself), Prow[(size_t)r * Kp + l_self]);
+        double u = inf;               // from +Inf with '>', so that a NaN candidate is ignored
+        if (u > vseed) u = vseed;
+        if (u > vself) u = vself;
+        ub[r] = u;
         if (!live || r >= rows_live) ub[r] = -inf;  // pad levels and rows beyond the table never ask for a block
     }
-    double ubmax = ub[0];
-#pragma unroll
-    for (int r = 1; r < TB; ++r) ubmax = ub[r] > ubmax ? ub[r] : ubmax;
     PH_LAP(1);
-    // ---- 2. which blocks can hold a minimum of some cell of this warp? --------------------------------------
-    unsigned int sneed = 0;
-    {
-        const double2 p01 = *reinterpret_cast<const double2 *>(pmw), p23 = *reinterpret_cast<const double2 *>(pmw + 2);
-        const double2 p45 = *reinterpret_cast<const double2 *>(pmw + 4), p67 = *reinterpret_cast<const double2 *>(pmw + 6);
-        const double pq[8] = {p01.x, p01.y, p23.x, p23.y, p45.x, p45.y, p67.x, p67.y};
-        double lbs[8];
+    // ---- 2. row test (lane = block) ------------------------------------------------------------------------
+    const float sf = __double2float_rd(s);
+    // slack of the level side: 2^-30 (|s| + largest finite jump cost), rounded up
+    const float sl_l = __fmul_ru(__fadd_ru(__double2float_ru(fabs(s)), cmx), 0x1p-30f);
+    float ubf[TB];
+    unsigned int cand = 0;
+    const int qlane = min(lane, nblk - 1);
 #pragma unroll
-        for (int Q = 0; Q < 8; ++Q) lbs[Q] = __dadd_rn(__dadd_rn(s, cms_l[(size_t)min(Q, nblk / SB - 1) * Kp]), pq[Q]);
-#pragma unroll
-        for (int Q = 0; Q < 8; ++Q) sneed |= ((lbs[Q] > ubmax || Q >= nblk / SB) ? 0u : 1u) << Q;
+    for (int r = 0; r < TB; ++r) {
+        ubf[r] = __double2float_ru(ub[r]);
+        float e = __fadd_ru(__double2float_ru(__dadd_ru(ub[r], -s)), sl_l);   // >= UB - s + slack in real arithmetic
+        if (!(e == e)) e = finf;                                             // NaN stage cost: prune nothing
+        const float U = key2f(__reduce_max_sync(0xffffffffu, f2key(e)));
+        const float pq = pmf[r * nblk + qlane];
+        const float slq = fminf(__fmul_ru(fabsf(pq), 0x1p-30f), fmax);        // slack of the block side
+        const float t = __fadd_rd(__fadd_rd(cw, pq), -slq);                   // <= cw + pm - slack in real arithmetic
+        cand |= __ballot_sync(0xffffffffu, lane < nblk && !(t > U));
     }
+    // ---- 3. level test (lane = level) on the candidate blocks -----------------------------------------------
     unsigned int pneed = 0;
-    for (unsigned int ms = __reduce_or_sync(0xffffffffu, sneed); ms;) {
-        // two surviving super-blocks per trip (the second may repeat the first): 8 independent exact tests
-        const int qa = (__ffs(ms) - 1) * SB;
-        ms &= ms - 1;
-        const int qb = ms ? (__ffs(ms) - 1) * SB : qa;
-        ms &= ms - 1;
-        double lbr[2 * SB][TB];
+    for (unsigned int ms = cand; ms;) {
+        int q[4];   // four candidate blocks per trip (the last one may repeat)
+        q[0] = __ffs(ms) - 1; ms &= ms - 1;
 #pragma unroll
-        for (int k = 0; k < 2 * SB; ++k) {
-            const int q = (k < SB ? qa : qb) + (k & (SB - 1));
-            const double amin = __dadd_rn(s, cm_l[(size_t)q * Kp]);
+        for (int k = 1; k < 4; ++k) { q[k] = ms ? __ffs(ms) - 1 : q[k - 1]; ms &= ms - 1; }
+        float a[4];
 #pragma unroll
-            for (int r = 0; r < TB; ++r) lbr[k][r] = __dadd_rn(amin, pmr[r * nblk + q]);
-        }
+        for (int k = 0; k < 4; ++k) a[k] = __fadd_rd(sf, cmf_l[(size_t)q[k] * Kp]);
 #pragma unroll
-        for (int k = 0; k < 2 * SB; ++k) {
-            const int q = (k < SB ? qa : qb) + (k & (SB - 1));
+        for (int k = 0; k < 4; ++k) {
             bool nd = false;
 #pragma unroll
-            for (int r = 0; r < TB; ++r) nd = nd || !(lbr[k][r] > ub[r]);
-            pneed |= (nd ? 1u : 0u) << q;
+            for (int r = 0; r < TB; ++r) nd = nd || !(__fadd_rd(a[k], pmf[r * nblk + q[k]]) > ubf[r]);
+            pneed |= (nd ? 1u : 0u) << q[k];
         }
     }
+    if (!live) pneed = 0;
     unsigned int m2 = __reduce_or_sync(0xffffffffu, pneed);
     PH_LAP(2);
-    // ---- 3. exhaustive scan of the surviving blocks, ascending, strict '>' -----------------------------------
+    // ---- 4. exhaustive scan of the surviving blocks, ascending, strict '>' -----------------------------------
 #pragma unroll
     for (int r = 0; r < TB; ++r) { best[r][0] = inf; arg[r][0] = MARKI; }
     auto candidates = [&](int q, double (&v)[TB][BK]) {
@@ -699,7 +743,7 @@ struct Finisher {
         const double inf = d_inf();
         const double *sn = sm.ss + (size_t)(T % 3) * Kp;
         const int *bn = sm.bts + (size_t)(T % 3) * Kp;
-        double *Pw = sm.Ps + (size_t)((n - 1) & 1) * R * Kp;
+        double *Pw = sm.Ps + (size_t)((n - 1) % kPsBufs) * R * Kp;
         // n == 1: only the terminal stage exists, it is the exit state (slot 1 of the reference); n == 2: it is slot 2
         double *phi = (n == 1) ? sl.phi : (n == 2) ? sl.phi + (size_t)B1 * Kp : nullptr;
         for (int unit = fw; unit < R * lblocks; unit += NF) {
@@ -718,8 +762,8 @@ struct Finisher {
         // my next rows receive the lower slices' block by TMA (issued by the comm warp): it must have landed before
         // my own results overwrite the cells I produce myself
         if (halo_on && i >= 2) {
-            mbar_wait_wd(&sm.mbar[MB_HALO + (i & 1)], (halo_phase >> (i & 1)) & 1u, c.err, c.wd_cycles);
-            halo_phase ^= 1u << (i & 1);
+            mbar_wait_wd(&sm.mbar[MB_HALO + (i % 3)], (halo_phase >> (i % 3)) & 1u, c.err, c.wd_cycles);
+            halo_phase ^= 1u << (i % 3);
         }
         // back-pressure: the successors consumed the ring slot this step overwrites
         long long tr0 = 0;
@@ -742,7 +786,7 @@ struct Finisher {
         a.pa = sm.pa;
         a.bt = sm.bts + (size_t)(T % 3) * Kp;
         a.umap = sm.umap;
-        a.Pn = sm.Ps + (size_t)((i - 1) & 1) * R * Kp;
+        a.Pn = sm.Ps + (size_t)((i - 1) % kPsBufs) * R * Kp;
         a.hring = c.halo + ((size_t)(T % kHaloRing) * B1 + r0) * Kp;
         a.phi = (i <= 2) ? sl.phi + ((size_t)((i + 1) & 1) * B1 + r0) * Kp : nullptr;
         a.argrow = reinterpret_cast<unsigned char *>(sl.arg) + ((size_t)(i - 1) * B1 + r0) * Kp * sizeof(ArgT);
@@ -833,13 +877,17 @@ __device__ __forceinline__ void scatter_warp(const Tables &t, const WaveCfg &c, 
 // A bounded watchdog turns a lost dependency into an error code instead of a hung GPU.
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 
-template <bool PROF>
+template <bool PROF, bool PIPE>
 __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane)
 {
+    // progress counters of the compute / finisher warps: one pair per CTA, or one pair per row group (group pipeline)
+    const int cgroups = PIPE ? c.RG : 1;
+    const uint64_t *w_fin = &sm.mbar[PIPE ? CNT_GFINISHED : CNT_FINISHED], *w_scn = &sm.mbar[PIPE ? CNT_GSCANNED : CNT_SCANNED];
+    const unsigned int fin_per = PIPE ? (unsigned int)(t.Kp >> 5) : (unsigned int)c.NF;
+    const unsigned int scn_per = PIPE ? (unsigned int)(t.Kp >> 5) : (unsigned int)((c.JS * c.tpg) >> 5);
     const int g = blockIdx.x;
     const int r0 = g * c.R;
-    const int Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n, NF = c.NF;
-    const int ncw = (c.JS * c.tpg) >> 5;
+    const int Kp = t.Kp, B1 = t.B1, R = c.R, n = t.n;
     const int btm = min(*c.btmax, B1 - 1);
     const int D = (btm + R - 1) / R;  // slices a push can span
     const int my_rows = min(R, B1 - r0);  // rows of this slice that exist in the table (>= 1)
@@ -870,11 +918,9 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
 
     for (;;) {
         bool progress = false;
-        const unsigned int fin_cnt = lds_acquire_u32(&sm.mbar[CNT_FINISHED]);  // NF arrivals per finished step
-        const unsigned int scn_cnt = lds_acquire_u32(&sm.mbar[CNT_SCANNED]);   // ncw arrivals per scanned stage
         pc[0] += 1;
         // ---- cost cursor --------------------------------------------------------------------------------
-        while (cT < Ttot && (cT < 3 || reached(fin_cnt, (unsigned int)(cT - 2) * (unsigned int)NF))) {
+        while (cT < Ttot && (cT < 3 || all_reached(w_fin, cgroups, fin_per, (unsigned int)(cT - 2)))) {
             if (lane == 0) {
                 const SlotDev &sl = c.slots[csub];
                 const int b = (int)(cT % 3);
@@ -901,16 +947,16 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
                 __syncwarp();  // every polling lane finished its acquire load; lane 0 inherits the order
                 pc[2] += 1;
             }
-            // the buffer the block lands in was last read by the scan of stage i+1 (or by the previous subproblem)
-            const int need_scanned = hsub * (n - 1) + hk - 1;
-            if (pred_seen >= hT && reached(scn_cnt, (unsigned int)need_scanned * (unsigned int)ncw)) {
+            // the buffer the block lands in was last read by the scan of stage i + kPsBufs - 1 (or by the previous subproblem)
+            const int need_scanned = hsub * (n - 1) + max(hk - (kPsBufs - 1), 0);
+            if (pred_seen >= hT && all_reached(w_scn, cgroups, scn_per, (unsigned int)need_scanned)) {
                 if (lane == 0) {
                     const int i = n - hk;
                     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy read
                     const uint32_t bytes = (uint32_t)((size_t)my_rows * Kp * sizeof(double));
-                    uint64_t *bar = &sm.mbar[MB_HALO + (i & 1)];
+                    uint64_t *bar = &sm.mbar[MB_HALO + (i % 3)];
                     mbar_expect_tx(bar, bytes);
-                    tma_load_1d(sm.Ps + (size_t)((i - 1) & 1) * R * Kp,
+                    tma_load_1d(sm.Ps + (size_t)((i - 1) % kPsBufs) * R * Kp,
                                 c.halo + ((size_t)(hT % kHaloRing) * B1 + r0) * Kp, bytes, bar);
                 }
                 if (++hk > n - 2) { hk = 1; if (++hsub >= c.nsub) h_active = false; }
@@ -964,19 +1010,40 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
 // Follows the scatter warps' counter; for every finished stage: fence.acq_rel.gpu so that the pushes made during
 // that stage are visible GPU-wide, then the relaxed store of the progress counter -- about 1 200 cycles that sit on
 // nobody's critical path.
-__device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane)
+template <bool BAR, bool PIPE>
+__device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c, const Smem &sm, int lane, int ncompute)
 {
-    if (lane != 0) return;
     const int g = blockIdx.x;
     const int n = t.n;
     unsigned long long *myflag = c.flags + (size_t)g * kFlagStride;
+    if constexpr (BAR) {
+        // Barrier hand-over (pruned tiles): this warp is a member of the stage barrier.  When the barrier completes, every
+        // push of the step is ordered before it; lane 0 then makes them visible GPU-wide (fence.acq_rel.gpu is cumulative
+        // over what the barrier ordered), publishes the step and counts it for the comm warp.  The compute warps never
+        // fence after their global stores.
+        const int Ttot = c.nsub * n;
+#pragma unroll 1
+        for (int T = 0; T < Ttot; ++T) {
+            asm volatile("bar.sync %0, %1;" ::"r"(kStageBarrier), "r"(ncompute + 32) : "memory");
+            if (lane == 0) {
+                if (T % n != 0) {  // the terminal stage pushes nothing
+                    fence_gpu();
+                    st_relaxed(myflag, (unsigned long long)T);
+                }
+                asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(&sm.mbar[CNT_FINISHED])), "r"((unsigned int)c.NF) : "memory");
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    if (lane != 0) return;
     int T = 0;
     for (int sub = 0; sub < c.nsub; ++sub) {
         ++T;  // the terminal stage pushes nothing
         for (int i = n - 1; i >= 1; --i, ++T) {
-            const unsigned int want = (unsigned int)(T + 1) * (unsigned int)c.NF;
             unsigned int spins = 0;
-            while (!reached(lds_acquire_u32(&sm.mbar[CNT_FINISHED]), want)) {
+            while (!all_reached(&sm.mbar[PIPE ? CNT_GFINISHED : CNT_FINISHED], PIPE ? c.RG : 1,
+                                PIPE ? (unsigned int)(t.Kp >> 5) : (unsigned int)c.NF, (unsigned int)(T + 1))) {
                 __nanosleep(BB_PUB_SLEEP);  // a quiet poll: this warp shares a scheduler with compute warps
                 if ((++spins & 0xffffu) == 0 && *(volatile int *)&c.err[3] && spins > (1u << 22)) return;  // stuck after an abort
             }
@@ -988,8 +1055,10 @@ __device__ __forceinline__ void publisher_warp(const Tables &t, const WaveCfg &c
 
 // MAXT is a multiple of 128: the register file is split evenly over the four schedulers, so the per-thread
 // budget is set by the scheduler that hosts the most warps.
-template <int TBA, int TBB, int TL, typename ArgT, int MAXT, bool PROF, int PR>
-__global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
+// KPC > 0: the padded level count Kp (= Kr for pruned tiles) is the compile-time constant KPC -- every row stride, block
+// count and table offset of the stage loop folds into immediates (the production shape K = 125 runs with KPC = 128).
+template <int TBA, int TBB, int TL, typename ArgT, bool PROF, int PR>
+__device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem sm;
@@ -1004,42 +1073,36 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
 
     // one-time: jump costs into shared memory, value rows to +Inf, barriers and counters
     for (int x = tid; x < c.Kr * Kp; x += blockDim.x) sm.cs[x] = x < K * Kp ? t.cost[x] : inf;  // pad rows: never win
-    for (int x = tid; x < 2 * R * Kp; x += blockDim.x) sm.Ps[x] = inf;
+    for (int x = tid; x < kPsBufs * R * Kp; x += blockDim.x) sm.Ps[x] = inf;
     {
         const int ul = 32 * c.EC, ubl = (Kp + ul - 1) / ul;  // levels per phase-C work unit, units per row
         for (int x = tid; x < R * ubl; x += blockDim.x) sm.umap[x] = ((x / ubl) << 16) | ((x % ubl) * ul);
     }
     if (tid == 0) {
-        for (int k = 0; k < 5; ++k) mbar_init(&sm.mbar[k], 1);  // cost[3], halo[2]: one arming arrival + tx bytes
+        for (int k = 0; k < 6; ++k) mbar_init(&sm.mbar[k], 1);  // cost[3], halo[3]: one arming arrival + tx bytes
         for (int v = 0; v < 2; ++v) {
             mbar_init(&sm.mbar[MB_SCANNED + v], NC >> 5);
             mbar_init(&sm.mbar[MB_FINISHED + v], c.NF);
         }
+        for (int k = 0; k < 2 * kMaxRowGroups; ++k) mbar_init(&sm.mbar[MB_GFIN + k], (unsigned)(Kp >> 5));
         sm.mbar[CNT_SCANNED] = 0;
         sm.mbar[CNT_FINISHED] = 0;
+        for (int k = 0; k < kMaxRowGroups; ++k) sm.mbar[CNT_GSCANNED + k] = sm.mbar[CNT_GFINISHED + k] = 0;
         sm.mbar[RING_OK] = (g + 1 < c.G) ? (uint64_t)(kHaloRing - 1) : (uint64_t)kNever;  // read as a 32-bit tick
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if constexpr (PR > 0) {  // block minima of the jump costs (pad rows are +Inf and never lower a minimum)
+    if constexpr (PR > 0) {  // block minima of the jump costs, rounded down to float (pad rows are +Inf and never lower a minimum)
         const int nblk = c.Kr / PR;
         for (int x = tid; x < nblk * Kp; x += blockDim.x) {
             const int q = x / Kp, l = x - q * Kp;
             double m = inf;
 #pragma unroll
             for (int jj = 0; jj < PR; ++jj) m = fmin(m, sm.cs[(size_t)(q * PR + jj) * Kp + l]);
-            sm.cmin[x] = m;
+            sm.cminf[x] = __double2float_rd(m);
         }
-        __syncthreads();
-        for (int x = tid; x < 8 * nblk + 64; x += blockDim.x) sm.pmin[x] = inf;  // rows the CTA does not own bound nothing
-        if (tid < 16) reinterpret_cast<int *>(sm.pmin + 8 * nblk + 64)[tid] = 0;
-        for (int x = tid; x < (nblk / 4) * Kp; x += blockDim.x) {
-            const int Q = x / Kp, l = x - Q * Kp;
-            double m = inf;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) m = fmin(m, sm.cmin[(size_t)(Q * 4 + k) * Kp + l]);
-            sm.cmins[x] = m;
-        }
+        for (int x = tid; x < 8 * nblk; x += blockDim.x) sm.pminf[x] = __int_as_float(0x7f800000);  // rows the CTA does not own bound nothing
+        if (tid < 16) reinterpret_cast<int *>(sm.pminf + 8 * nblk)[tid] = 0;
         __syncthreads();
     }
 
@@ -1048,11 +1111,11 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         return;
     }
     if (tid >= NC + 32) {
-        publisher_warp(t, c, sm, tid - NC - 32);
+        publisher_warp<(PR > 0 && BB_BAR_HANDOVER != 0), (PR > 0 && BB_GROUP_PIPE != 0)>(t, c, sm, tid - NC - 32, NC);
         return;
     }
     if (tid >= NC) {
-        comm_warp<PROF>(t, c, sm, tid - NC);
+        comm_warp<PROF, (PR > 0 && BB_GROUP_PIPE != 0)>(t, c, sm, tid - NC);
         return;
     }
 
@@ -1088,10 +1151,24 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         if (lane == 0) {
             fence_cta();
             mbar_arrive_relaxed(&sm.mbar[MB_SCANNED + v]);
-            if (v == NV - 1) reds_relaxed_inc(&sm.mbar[CNT_SCANNED]);
+            if (v == NV - 1) reds_relaxed_inc(&sm.mbar[(PR > 0 && BB_GROUP_PIPE != 0) ? CNT_GSCANNED + pr_grp : CNT_SCANNED]);
         }
     };
     const int rowA = PR > 0 ? pr_grp * TBA : rg * TBA, rowB = PR > 0 ? 0 : c.RA + rg * TBB;
+    // pruned scan, once per launch: (lane = block q) the smallest block minimum of the jump costs over the live levels of this
+    // warp's level block; (lane = level) the largest finite jump cost into my level, rounded up
+    float pr_cw = __int_as_float(0x7f800000), pr_cmx = 0.f;
+    if constexpr (PR > 0) {
+        const int nblk = c.Kr / PR, l0 = ((tid >> 5) % nLB) << 5;
+        if (lane < nblk)
+#pragma unroll 1
+            for (int l = l0; l < min(l0 + 32, K); ++l) pr_cw = fminf(pr_cw, sm.cminf[(size_t)lane * Kp + l]);
+#pragma unroll 1
+        for (int j = 0; j < K; ++j) {
+            const double cj = sm.cs[(size_t)j * Kp + lg];
+            if (fabs(cj) < inf) pr_cmx = fmaxf(pr_cmx, __double2float_ru(fabs(cj)));
+        }
+    }
     unsigned int executed = 0;  // pruned scan: blocks this warp really scanned
     long long ph[4] = {0, 0, 0, 0};  // profile of the pruned scan: block minima + seed, upper bounds, masks, scan
     ArgT *pa = reinterpret_cast<ArgT *>(sm.pa);
@@ -1102,12 +1179,20 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
     const int cwarp = tid >> 5;
     Finisher<ArgT, PROF> fin(t, c, sm, cwarp, NC >> 5, lane);
     uint32_t scanned_phase = 0;
+    constexpr bool kBarHandover = PR > 0 && BB_BAR_HANDOVER != 0;
+    constexpr bool kGroupPipe = PR > 0 && BB_GROUP_PIPE != 0;
     auto finished = [&]() {
-        __syncwarp();
-        if (lane == 0) {
-            fence_cta();
-            mbar_arrive_relaxed(&sm.mbar[MB_FINISHED]);
-            reds_relaxed_inc(&sm.mbar[CNT_FINISHED]);
+        if constexpr (kBarHandover) {
+            // one barrier of the compute warps + the publisher: orders this stage's value rows (shared memory) for the next
+            // scan and the pushes for the publisher's fence; no CTA-scope fence behind the global stores
+            asm volatile("bar.sync %0, %1;" ::"r"(kStageBarrier), "r"(NC + 32) : "memory");
+        } else {
+            __syncwarp();
+            if (lane == 0) {
+                fence_cta();
+                mbar_arrive_relaxed(&sm.mbar[MB_FINISHED]);
+                reds_relaxed_inc(&sm.mbar[kGroupPipe ? CNT_GFINISHED + pr_grp : CNT_FINISHED]);
+            }
         }
     };
 
@@ -1120,37 +1205,67 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             finished();
         }
         ++T;
+        if constexpr (kGroupPipe) wait_finished(0);  // the terminal stage is written by all warps together
         for (int i = n - 1; i >= 1; --i, ++T) {
-            const double *Pc = sm.Ps + (size_t)(i & 1) * R * Kp;
+            const double *Pc = sm.Ps + (size_t)(i % kPsBufs) * R * Kp;
             const double *ssc = sm.ss + (size_t)(T % 3) * Kp;
             wait_costs(T);
             // ---- phase B: register-tiled min-plus scan over this group's successors, sub-slice A then B ------
-            wait_finished(0);  // rows of A for stage i are complete (finish(A, i+1) or the terminal stage)
+            if constexpr (kGroupPipe) {
+                // my rows for stage i are complete once the row groups 0 .. mine have scattered stage i+1
+                if (i < n - 1) {
+                    const int par1 = i & 1 ? 0 : 1;  // (i + 1) & 1
+                    const int cnt_p = par1 ? n / 2 : (n - 1) / 2;  // stages of that parity per subproblem
+                    const uint32_t parity = (uint32_t)(sub * cnt_p + ((n - 2 - i) >> 1)) & 1u;
+                    for (int j = 0; j <= pr_grp; ++j) mbar_wait_wd(&sm.mbar[MB_GFIN + 2 * j + par1], parity, c.err, c.wd_cycles);
+                }
+            } else if constexpr (!kBarHandover) {
+                wait_finished(0);  // rows of A for stage i are complete (finish(A, i+1) or the terminal stage)
+            }
             PROF_LAP(0);
             if constexpr (PR > 0) {
                 // ---- pruned scan: block minima of my rows, branch-and-bound scan, scatter from registers ----------
                 static_assert(TL == 1, "pruned scan: a lane is a level");
                 const int nblk = c.Kr / PR;
-                double *pmR = sm.pmin, *pmsR = sm.pmin + 8 * nblk;
-                int *qseed = reinterpret_cast<int *>(sm.pmin + 8 * nblk + 64);
-                double *pmw = sm.pmin + 8 * nblk + 72 + (tid >> 5) * 8;
+                float *pmR = sm.pminf;
+                int *qseed = reinterpret_cast<int *>(sm.pminf + 8 * nblk);
                 // block minima and seed of the rows of my row group, once per stage: the group's warps (one per level block)
                 // share its rows, then meet at the group's own named barrier (not a CTA-wide one)
                 for (int r = rowA + (tid >> 5) % nLB; r < min(rowA + TBA, R); r += nLB)
-                    row_minima<PR>(Pc + (size_t)r * Kp, pmR + r * nblk, pmsR + r * 8, qseed + r, nblk, lane);
+                    row_minima<PR>(Pc + (size_t)r * Kp, pmR + r * nblk, qseed + r, nblk, lane);
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + pr_grp), "r"(32 * nLB) : "memory");
                 const FinishArgs fa = fin.stage_args(sl, i, T);
                 double best[TBA][1];
                 int arg[TBA][1];
-                scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cmin + lg, sm.cmins + lg, pmR + rowA * nblk,
-                                                 pmsR + rowA * 8, qseed + rowA, pmw, ssc[lg], nblk, Kp, active,
-                                                 min(R, t.B1 - fin.r0) - rowA, lane, min(lg, K - 1), best, arg, executed, ph);
+                scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cminf + lg, pmR + rowA * nblk, qseed + rowA,
+                                                 ssc[lg], pr_cw, pr_cmx, nblk, Kp, active, min(R, t.B1 - fin.r0) - rowA, lane,
+                                                 min(lg, K - 1), best, arg, executed, ph);
                 PROF_LAP(1);
                 scanned(0);  // the comm warp may refill the rows this stage read
                 fin.wait_inputs(i, T);
+                if constexpr (kGroupPipe) {
+                    // my results go into the buffer stage i+1 read: every warp must have scanned it.  A landed halo block
+                    // proves that (the comm warp issues it after the last scan); slices without one check the counter.
+                    if (!(fin.halo_on && i >= 2)) {
+                        unsigned int spins = 0;
+                        while (!all_reached(&sm.mbar[CNT_GSCANNED], c.RG, (unsigned int)nLB, (unsigned int)(sub * (n - 1) + (n - 1 - i)))) {
+                            __nanosleep(32);
+                            if ((++spins & 0xfffffu) == 0 && *(volatile int *)&c.err[3]) break;
+                        }
+                    }
+                }
                 PROF_LAP(2);
                 scatter_tile<TBA, 1, ArgT>(fa, rowA, lg, best, arg);  // pad levels only write their MARK bytes
-                finished();
+                if constexpr (kGroupPipe) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_cta();
+                        mbar_arrive_relaxed(&sm.mbar[MB_GFIN + 2 * pr_grp + (i & 1)]);
+                        reds_relaxed_inc(&sm.mbar[CNT_GFINISHED + pr_grp]);
+                    }
+                } else {
+                    finished();
+                }
                 PROF_LAP(3);
                 pc[4] += 1;
                 continue;
@@ -1199,7 +1314,12 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
             pc[4] += 1;
         }
         // drain: stage 1 (or the terminal stage when n == 1) is finished; keeps the barrier phases aligned
-        for (int v = 0; v < NV; ++v) wait_finished(v);
+        if constexpr (kGroupPipe) {
+            // every warp of the CTA has scattered stage 1: the next subproblem's terminal stage may overwrite the rows
+            asm volatile("bar.sync %0, %1;" ::"r"(kStageBarrier), "r"(NC) : "memory");
+        } else if constexpr (!kBarHandover) {
+            for (int v = 0; v < NV; ++v) wait_finished(v);
+        }
     }
     if constexpr (PR > 0) {  // candidates really evaluated: blocks x successors x rows x live lanes of this warp
         if (c.exec && lane == 0) {
@@ -1228,6 +1348,20 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(Tables t, WaveCfg c)
         c.prof[(size_t)g * 16 + 4] = pc[4];
     }
 #undef PROF_LAP
+}
+
+template <int TBA, int TBB, int TL, typename ArgT, int MAXT, bool PROF, int PR, int KPC = 0>
+__global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(const __grid_constant__ Tables t_in, const __grid_constant__ WaveCfg c_in)
+{
+    if constexpr (KPC > 0) {
+        Tables t = t_in;
+        WaveCfg c = c_in;
+        t.Kp = KPC;
+        c.Kr = KPC;
+        wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t, c);
+    } else {
+        wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t_in, c_in);
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -1343,7 +1477,7 @@ bool wave_configure(const Tables &t, int argw, int num_sms, size_t smem_max, int
                 if (gmax > num_sms) gmax = num_sms;
                 WaveCfg c = cfg;
                 fill_geometry(t, argw, gmax, js, v, ns, c);
-                if (pr > 0 && (c.G > gmax || c.threads > pruned_max_threads(kVariants[v].TBA, kVariants[v].TBB))) continue;  // rows x CTAs must cover the table
+                if (pr > 0 && (c.G > gmax || c.RG > kMaxRowGroups || c.threads > pruned_max_threads(kVariants[v].TBA, kVariants[v].TBB))) continue;  // rows x CTAs must cover the table
                 if (pr == 0 && c.threads > kWaveThreads) continue;
                 if (c.smem > smem_max) continue;
                 if ((size_t)c.JS * c.R * t.Kp >= ((size_t)1 << 30) || (size_t)t.B1 * t.Kp >= ((size_t)1 << 31) ||
@@ -1421,6 +1555,11 @@ static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStrea
     // the cycle counters are a separate instantiation: their code would cost the production kernel ~1.5 %
     const void *fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR>
                               : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR>;
+    if constexpr (PR > 0 && TBA == 2 && TBB >= 7) {  // the tiles of the production shape: Kp as a compile-time constant
+        if (BB_KPC != 0 && t.Kp == 128 && cfg.Kr == 128)
+            fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR, 128>
+                          : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 128>;
+    }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     // cooperative launch: the CTAs wait on one another, so all of them must be co-resident

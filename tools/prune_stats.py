@@ -55,7 +55,11 @@ for i in range(n - 2, -1, -1):
         UB = np.minimum(vblk[np.arange(B1), :, seed], v[:, np.arange(K), np.arange(K)])   # [b'][l]
         LB = (s[None, :, None] + cminq.T[None, :, :]) + pm[:, None, :]                   # [b'][l][q]
         need = ~(LB > UB[:, :, None])                                                  # [b'][l][q]
-        cnt = dict(exact=0, super=0, rowlane=0, rowlane_any=0, tiles=0, exact_cells=0.0)
+        jstar = np.argmin(np.where(np.isnan(Ppad), np.inf, Ppad), axis=1)                # [b']  the row's smallest value
+        UB1 = np.minimum(v[np.arange(B1), :, np.minimum(jstar, K - 1)], v[:, np.arange(K), np.arange(K)])
+        need1 = ~(LB > UB1[:, :, None])
+        needp = ~(LB > best[:, :, None])                                               # a perfect upper bound: the minimum itself
+        cnt = dict(exact=0, exact1=0, perfect=0, super=0, rowlane=0, rowlane_any=0, tiles=0, exact_cells=0.0)
         for b0 in range(0, B1 - RW + 1, RW * 5):                      # a sample of row groups
             rows = slice(b0, b0 + RW)
             for l0 in range(0, K, 32):
@@ -63,6 +67,8 @@ for i in range(n - 2, -1, -1):
                 nd = need[rows, ls, :]
                 ex = nd.any(axis=(0, 1))
                 cnt["exact"] += ex.sum()
+                cnt["exact1"] += need1[rows, ls, :].any(axis=(0, 1)).sum()
+                cnt["perfect"] += needp[rows, ls, :].any(axis=(0, 1)).sum()
                 # super-block coarse test of the round-2 kernel: rows merged, ubmax
                 pms = pm[rows].reshape(RW, nbr // 4, 4).min(axis=(0, 2))                 # [Q]
                 cms = cminq.reshape(nbr // 4, 4, K).min(axis=1)[:, ls]                  # [Q][l]
@@ -78,7 +84,7 @@ for i in range(n - 2, -1, -1):
                 cnt["rowlane_any"] += rl.sum() / RW
                 cnt["tiles"] += 1
         t = cnt["tiles"]
-        print(f"stage {i:6d}: per tile of {nbr} blocks: exact {cnt['exact']/t:5.2f}  super(r2 coarse) {cnt['super']/t:5.2f}  "
+        print(f"stage {i:6d}: per tile of {nbr} blocks: exact {cnt['exact']/t:5.2f}  exact(UB from j* and self only) {cnt['exact1']/t:5.2f}  perfect-UB {cnt['perfect']/t:5.2f}  super(r2 coarse) {cnt['super']/t:5.2f}  "
               f"rowlane(union rows) {cnt['rowlane']/t:5.2f}  rowlane(per row) {cnt['rowlane_any']/t:5.2f}", flush=True)
     Pn = np.full_like(P, np.inf)
     for l in range(K):
