@@ -430,6 +430,7 @@ def run_ours(args):
                     "l2": "every step streams a (n-1)*(B+1)*128-byte argmin table (12.8 GB at full size) through L2, "
                           "far larger than the 126 MB L2; no separate flush",
                     "kernel_path": int(stats["path"]), "ctas": int(stats["ctas"]), "rows_per_cta": int(stats["rows_per_cta"]),
+                    "ctas_with_full_rows": int(stats["ctas_full_rows"]), "rows_per_cta_upper_zone": int(stats["rows_per_cta_top"]),
                     "threads_per_cta": int(stats["threads"]), "jsplit": int(stats["jsplit"])})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,

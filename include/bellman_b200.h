@@ -237,6 +237,7 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *  18 block size of the pruned scan of the current geometry (0: exhaustive scan)
  *  19 1 if the plan went back to the exhaustive tiles because its DP evaluated more candidates than the measured
  *     break-even of the pruned scan (13 %): a data / horizon dependent choice, results are identical either way
+ *  20 CTAs that own (5) source rows; the CTAs above them own (21) rows (two-zone slices; 20 == 4: uniform slices)
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);
 
@@ -263,7 +264,8 @@ int bb200_plan_tune(bb200_plan *plan, int32_t ctas, int32_t jsplit, int32_t vari
  *   2 rows per thread tile in sub-slice A   3 in sub-slice B (0: one sub-slice)   4 levels per thread tile
  *   5 CTAs   6 source rows per CTA   7 j-split   8 successors per j-group   9 rows of the padded jump-cost table
  *  10 scatter warps   11 threads per CTA   12 dynamic shared memory per CTA [bytes]
- *  13 block size of the pruned scan (0: exhaustive scan) */
+ *  13 block size of the pruned scan (0: exhaustive scan)
+ *  14 CTAs that own (6) rows; the CTAs above them own (15) rows (two-zone slices; 14 == 5: uniform slices) */
 int bb200_wave_geometry(int64_t n, int32_t M, int32_t K, int64_t B, int32_t num_sms, int64_t smem_max, int32_t ctas,
                         int32_t jsplit, int32_t variant, int64_t *out, int32_t count);
 

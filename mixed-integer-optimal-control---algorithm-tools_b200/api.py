@@ -173,11 +173,12 @@ class TRMPlan:
         return v.value
 
     def stats(self):
-        out = np.zeros(20, dtype=np.float64)
-        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 20))
+        out = np.zeros(22, dtype=np.float64)
+        _lib.check(self.lib.bb200_stats(self._h, _lib.f64p(out), 22))
         keys = ("dp_ms", "backtrack_ms", "launches", "path", "ctas", "rows_per_cta", "arg_bytes",
                 "device_bytes", "threads", "jsplit", "wave_ms", "graph_replays", "variant", "scatter_warps",
-                "batch_ms", "batch_waves", "batch_syncs", "executed_updates", "prune_block", "prune_switched_off")
+                "batch_ms", "batch_waves", "batch_syncs", "executed_updates", "prune_block", "prune_switched_off",
+                "ctas_full_rows", "rows_per_cta_top")
         return dict(zip(keys, out.tolist()))
 
     def profile(self, enable=True, fetch=False, max_ctas=148):

@@ -614,9 +614,9 @@ int bb200_wave_geometry(int64_t n, int32_t M, int32_t K, int64_t B, int32_t num_
     t.n = (int)n; t.M = M; t.K = K; t.Kp = (K + 31) / 32 * 32; t.B1 = (int)B + 1; t.dt = 1.0;
     WaveCfg c{};
     const bool ok = wave_configure(t, K <= 255 ? 1 : 2, num_sms, (size_t)smem_max, ctas, jsplit, variant, c);
-    const int64_t v[14] = {ok ? 1 : 0, ok ? c.variant + 1 : 0, c.TB, c.TBB, c.TL, c.G, c.R, c.JS, c.jper, c.Kr, c.NS,
-                           c.threads, (int64_t)c.smem, c.PR};
-    for (int k = 0; k < count && k < 14; ++k) out[k] = ok || k == 0 ? v[k] : 0;
+    const int64_t v[16] = {ok ? 1 : 0, ok ? c.variant + 1 : 0, c.TB, c.TBB, c.TL, c.G, c.R, c.JS, c.jper, c.Kr, c.NS,
+                           c.threads, (int64_t)c.smem, c.PR, c.GA, c.Rtop};
+    for (int k = 0; k < count && k < 16; ++k) out[k] = ok || k == 0 ? v[k] : 0;
     return BB200_OK;
 }
 
@@ -1102,15 +1102,16 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
         CU(cudaStreamSynchronize(plan->stream));
         CU(cudaMemcpy(&exec, plan->d_exec, sizeof exec, cudaMemcpyDeviceToHost));
     }
-    const double v[20] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
+    const double v[22] = {plan->last_dp_ms, plan->last_bt_ms, plan->launches, (double)plan->last_path,
                           plan->wave_ok ? (double)plan->cfg.G : 0., plan->wave_ok ? (double)plan->cfg.R : 0.,
                           (double)plan->argw, (double)plan->dev_bytes,
                           plan->wave_ok ? (double)plan->cfg.threads : 0., plan->wave_ok ? (double)plan->cfg.JS : 0.,
                           plan->last_wave_ms, plan->graph_replays,
                           plan->wave_ok ? (double)(plan->cfg.variant + 1) : 0., plan->wave_ok ? (double)plan->cfg.NS : 0.,
                           plan->last_batch_ms, plan->batch_waves, plan->batch_syncs, (double)exec,
-                          plan->wave_ok ? (double)plan->cfg.PR : 0., plan->prune_switches};
-    for (int k = 0; k < count && k < 20; ++k) out[k] = v[k];
+                          plan->wave_ok ? (double)plan->cfg.PR : 0., plan->prune_switches,
+                          plan->wave_ok ? (double)plan->cfg.GA : 0., plan->wave_ok ? (double)plan->cfg.Rtop : 0.};
+    for (int k = 0; k < count && k < 22; ++k) out[k] = v[k];
     return BB200_OK;
 }
 

@@ -25,6 +25,7 @@ struct WaveCfg {
     int G;        // CTAs (each owns R consecutive source budget rows)
     int RG;       // row groups per sub-slice
     int R;        // RA + RB
+    int GA, Rtop; // two-zone slices (pruned tiles): CTAs 0 .. GA-1 own R source rows, the CTAs above them Rtop; GA = G: uniform
     int RA, RB;   // rows of sub-slice A (lower) and B (upper): RG * TB, RG * TBB
     int nLG;      // level groups = ceil(K / TL)
     int JS;       // j-split: thread groups scanning disjoint successor ranges

@@ -12,24 +12,25 @@ import mioc_b200 as m
 
 SMEM_MAX = 232448   # opt-in dynamic shared memory per CTA on sm_100 (227 KB)
 FIELDS = ("ok", "variant", "tba", "tbb", "tl", "ctas", "rows", "jsplit", "jper", "kr", "scatter_warps", "threads", "smem",
-          "prune")
+          "prune", "ctas_full", "rows_top")
 
 
 def geometry(n, M, K, B, sms=148, smem=SMEM_MAX, ctas=0, jsplit=0, variant=0):
     lib = importlib.import_module(m.__name__ + "._lib").load()
-    out = np.zeros(14, dtype=np.int64)
+    out = np.zeros(16, dtype=np.int64)
     rc = lib.bb200_wave_geometry(n, M, K, B, sms, smem, ctas, jsplit, variant,
-                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 14)
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 16)
     assert rc == 0
     return dict(zip(FIELDS, out.tolist()))
 
 
 def test_config4_geometry_is_pinned():
-    # default: the pruned (branch-and-bound) scan -- lane = level, 2 rows per warp, 7 rows per CTA in 4 row groups,
-    # 4 level blocks x 4 row groups = 16 compute warps + comm + publisher, blocks of 4 successors
+    # default: the pruned (branch-and-bound) scan -- lane = level, 2 rows per warp, 4 level blocks x 4 row groups = 16 compute
+    # warps + comm + publisher, blocks of 4 successors; two-zone slices on all 148 SMs: 56 CTAs x 8 rows, 92 CTAs x 6 rows
     g = geometry(100_000, 3, 125, 999)
     assert g["ok"] == 1 and g["prune"] == 4
-    assert (g["tba"], g["tbb"], g["tl"]) == (2, 7, 1) and (g["ctas"], g["rows"]) == (143, 7)
+    assert (g["tba"], g["tbb"], g["tl"]) == (2, 8, 1) and (g["ctas"], g["rows"]) == (148, 8)
+    assert (g["ctas_full"], g["rows_top"]) == (56, 6) and 56 * 8 + 92 * 6 == 1000
     assert (g["jsplit"], g["kr"], g["scatter_warps"], g["threads"]) == (1, 128, 0, 576) and g["smem"] <= SMEM_MAX
     # variant -1 = what the plan falls back to when the bound test does not pay on its data: the exhaustive tiles
     g = geometry(100_000, 3, 125, 999, variant=-1)
@@ -50,8 +51,11 @@ def test_geometry_invariants(K, B, n, sms):
         pytest.skip("shape runs on the per-stage kernels")
     Kp = (K + 31) // 32 * 32
     assert 1 <= g["ctas"] <= sms
-    assert g["ctas"] * g["rows"] >= B + 1                      # every source row has an owner
-    assert (g["ctas"] - 1) * g["rows"] < B + 1                 # and no CTA is empty
+    ga, rt = g["ctas_full"], g["rows_top"]
+    assert 0 <= ga <= g["ctas"] and 1 <= rt <= g["rows"]
+    assert ga * g["rows"] + (g["ctas"] - ga) * rt >= B + 1     # every source row has an owner
+    last_r0 = ga * g["rows"] + (g["ctas"] - 1 - ga) * rt if ga < g["ctas"] else (g["ctas"] - 1) * g["rows"]
+    assert last_r0 < B + 1                                     # and no CTA is empty
     if g["prune"]:
         assert g["rows"] == g["tbb"] and g["jsplit"] == 1 and g["scatter_warps"] == 0 and g["kr"] % 32 == 0
     else:
