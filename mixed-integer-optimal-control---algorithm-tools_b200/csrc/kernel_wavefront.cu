@@ -207,7 +207,9 @@ struct Smem {
     float *cminf;     // pruned scan: [Kr/PR][Kp] block minima of the jump costs ROUNDED DOWN to float,
                       //              cminf[q][l] <= min_{j in block q} c_jl
     float *pminf;     // pruned scan: block minima of the CTA's value rows rounded down to float [8][Kr/PR], then the rows' seed
-                      //              blocks int[16]
+                      //              successors int[16], then two per-launch tables: cw[Kp/32][32] (level block, block q: the
+                      //              smallest cminf[q][l] over the live levels of the level block) and cmx[Kp] (the largest
+                      //              finite |jump cost| into level l, rounded up)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -234,7 +236,7 @@ __host__ __device__ inline size_t carve(const Tables &t, const WaveCfg &c, int a
                              (size_t)js_smem * c.R * t.Kp * (size_t)argw,
                              (size_t)c.R * (t.Kp / 32) * sizeof(int),
                              (size_t)nblk * t.Kp * sizeof(float),
-                             c.PR ? (size_t)(8 * nblk + 16) * sizeof(float) : 0};
+                             c.PR ? (size_t)(8 * nblk + 16 + 2 * t.Kp) * sizeof(float) : 0};
     for (int k = 0; k < 10; ++k) {
         o[k] = off;
         off = align_up(off + sizes[k], 128);
@@ -1085,18 +1087,22 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
     const int jb = jg * c.jper;
     const int je = min(c.Kr, jb + c.jper);  // rows K .. Kr-1 of the cost table are +Inf: (s + Inf) + P never wins
     const int lane = tid & 31;
-    uint32_t cost_phase = 0, fin_phase = 0;
+    uint32_t fin_phase = 0;
+    int T = 0;  // global step: subproblem * n + (n - stage)
     long long pc[5] = {0, 0, 0, 0, 0};  // profile: wait A (+ costs), phase B, hand-over, wait B, stages
     long long tp = clock64();
 #define PROF_LAP(k) do { if constexpr (PROF) { if (c.prof) { const long long tq = clock64(); pc[k] += tq - tp; tp = tq; } } } while (0)
     auto wait_costs = [&](int T) {
-        const int b = (int)(T % 3);
-        mbar_wait_wd(&sm.mbar[MB_COST + b], (cost_phase >> b) & 1u, c.err, c.wd_cycles);
-        cost_phase ^= 1u << b;
+        const int b = (int)(T % 3);   // step T is completion number T / 3 of barrier T % 3: no phase word to keep in a register
+        mbar_wait_wd(&sm.mbar[MB_COST + b], (uint32_t)(T / 3) & 1u, c.err, c.wd_cycles);
     };
     auto wait_finished = [&](int v) {
-        mbar_wait_wd(&sm.mbar[MB_FINISHED + v], (fin_phase >> v) & 1u, c.err, c.wd_cycles);
-        fin_phase ^= 1u << v;
+        if constexpr (PR > 0) {  // one hand-over per step: the wait before step T is completion number T - 1
+            mbar_wait_wd(&sm.mbar[MB_FINISHED], (uint32_t)(T - 1) & 1u, c.err, c.wd_cycles);
+        } else {
+            mbar_wait_wd(&sm.mbar[MB_FINISHED + v], (fin_phase >> v) & 1u, c.err, c.wd_cycles);
+            fin_phase ^= 1u << v;
+        }
     };
     auto scanned = [&](int v) {
         __syncwarp();
@@ -1108,18 +1114,25 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
     };
     const int rowA = PR > 0 ? pr_grp * TBA : rg * TBA, rowB = PR > 0 ? 0 : c.RA + rg * TBB;
     // pruned scan, once per launch: (lane = block q) the smallest block minimum of the jump costs over the live levels of this
-    // warp's level block; (lane = level) the largest finite jump cost into my level, rounded up
-    float pr_cw = __int_as_float(0x7f800000), pr_cmx = 0.f;
+    // warp's level block; (lane = level) the largest finite jump cost into my level, rounded up.  Kept in shared memory and
+    // re-read every stage: two registers less in a kernel that is capped at 96.
     if constexpr (PR > 0) {
         const int nblk = c.Kr / PR, l0 = ((tid >> 5) % nLB) << 5;
-        if (lane < nblk)
+        float *cwv = sm.pminf + 8 * nblk + 16, *cmxv = cwv + Kp;
+        if (pr_grp == 0) {
+            float cw = __int_as_float(0x7f800000), cmx = 0.f;
+            if (lane < nblk)
 #pragma unroll 1
-            for (int l = l0; l < min(l0 + 32, K); ++l) pr_cw = fminf(pr_cw, sm.cminf[(size_t)lane * Kp + l]);
+                for (int l = l0; l < min(l0 + 32, K); ++l) cw = fminf(cw, sm.cminf[(size_t)lane * Kp + l]);
 #pragma unroll 1
-        for (int j = 0; j < K; ++j) {
-            const double cj = sm.cs[(size_t)j * Kp + lg];
-            if (fabs(cj) < inf) pr_cmx = fmaxf(pr_cmx, __double2float_ru(fabs(cj)));
+            for (int j = 0; j < K; ++j) {
+                const double cj = sm.cs[(size_t)j * Kp + lg];
+                if (fabs(cj) < inf) cmx = fmaxf(cmx, __double2float_ru(fabs(cj)));
+            }
+            cwv[l0 + lane] = cw;
+            cmxv[lg] = cmx;
         }
+        asm volatile("bar.sync %0, %1;" ::"r"(kMaxRowGroups + 1), "r"(NC) : "memory");  // compute warps only
     }
     unsigned int executed = 0;  // pruned scan: blocks this warp really scanned
     long long ph[4] = {0, 0, 0, 0};  // profile of the pruned scan: block minima + seed, upper bounds, masks, scan
@@ -1141,7 +1154,6 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
         }
     };
 
-    int T = 0;
     for (int sub = 0; sub < c.nsub; ++sub) {
         const SlotDev sl = c.slots[sub];
         wait_costs(T);  // terminal stage: nothing to scan, but every role follows every cost phase
@@ -1184,7 +1196,7 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
                 double best[TBA][1];
                 int arg[TBA][1];
                 scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cminf + lg, pmR + rowA * nblk, qseed + rowA,
-                                                 ssc[lg], pr_cw, pr_cmx, nblk, Kp, active, pr_rows_live, lane,
+                                                 ssc[lg], sm.pminf[8 * nblk + 16 + lg], sm.pminf[8 * nblk + 16 + Kp + lg], nblk, Kp, active, pr_rows_live, lane,
                                                  min(lg, K - 1), best, arg, executed, ph);
                 PROF_LAP(1);
                 scanned(0);  // the comm warp may refill the rows this stage read
@@ -1294,12 +1306,16 @@ struct Variant { int TBA, TBB, TL, PR; };
 // levels x TBA consecutive rows, and the second column is the number of rows of the CTA (the last row group may be ragged:
 // 7 rows = 4 + 3 or 2 + 2 + 2 + 1); the row groups run side by side on different warps and the compute warps finish their
 // own stage.  Built for 4 * ceil(rows / TBA) compute warps + comm + publisher.
+#ifdef BB_FAST_BUILD   // register / SASS checks of the production tile only (nvcc -cubin -DBB_FAST_BUILD): not a usable library
+#define BB200_VARIANTS(X) X(27, 2, 8, 1, 4)
+#else
 #define BB200_VARIANTS(X)                                                                                      \
     X(0, 7, 0, 2, 0) X(1, 8, 0, 2, 0) X(2, 6, 0, 2, 0) X(3, 5, 0, 2, 0) X(4, 4, 0, 2, 0) X(5, 3, 0, 2, 0) X(6, 2, 0, 2, 0) X(7, 1, 0, 2, 0) \
     X(8, 8, 0, 1, 0) X(9, 4, 0, 1, 0) X(10, 2, 0, 1, 0) X(11, 1, 0, 1, 0)                                                    \
     X(12, 4, 3, 2, 0) X(13, 4, 4, 2, 0) X(14, 3, 3, 2, 0) X(15, 3, 2, 2, 0) X(16, 2, 2, 2, 0) X(17, 2, 1, 2, 0) X(18, 1, 1, 2, 0)     \
     X(19, 4, 4, 1, 0) X(20, 2, 2, 1, 0) X(21, 1, 1, 1, 0) X(22, 4, 3, 1, 0) X(23, 3, 3, 1, 0)                               \
     X(24, 4, 7, 1, 4) X(25, 2, 7, 1, 4) X(26, 4, 8, 1, 4) X(27, 2, 8, 1, 4) X(28, 2, 4, 1, 4) X(29, 1, 2, 1, 4) X(30, 4, 4, 1, 4) X(31, 3, 6, 1, 4)
+#endif
 static const Variant kVariants[] = {
 #define X(idx, a, b, l, pr) {a, b, l, pr},
     BB200_VARIANTS(X)
