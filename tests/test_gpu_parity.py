@@ -138,7 +138,11 @@ def test_synthetic_config4_shape_vs_oracle(gpu_lib, oracle, tie):
                                   dict(variant=822, jsplit=2),
                                   # pruned (branch-and-bound) scan: 4+4 rows fit the 212 budget rows on 27 CTAs etc.
                                   dict(variant=25), dict(variant=26), dict(variant=27), dict(variant=28),
-                                  dict(variant=29), dict(variant=30), dict(variant=31), dict(variant=32)])
+                                  dict(variant=29), dict(variant=30), dict(variant=31), dict(variant=32),
+                                  # two-zone slices (the upper CTAs own one row group less): 16 x 8 + 14 x 6, 26 x 8 + 1 x 4,
+                                  # 6 x 4 + 94 x 2 and 106 x 2 rows = the 212 budget rows
+                                  dict(ctas=30, variant=28), dict(ctas=27, variant=27), dict(ctas=100, variant=29),
+                                  dict(ctas=106, variant=29)])
 def test_wavefront_geometries(gpu_lib, oracle, tune):
     """Every tile variant / CTA count / j-split / scatter-warp count (variant + 100 * NS) of the pipelined kernel
     gives identical bits."""
@@ -154,7 +158,8 @@ def test_wavefront_geometries(gpu_lib, oracle, tune):
                                            (10, 2, 333, dict(ctas=148, variant=614, jsplit=2)),
                                            (9, 2, 150, dict(variant=25)), (33, 1, 97, dict(variant=27)),   # pruned scan
                                            (7, 1, 40, dict(variant=29)), (10, 2, 333, dict(variant=26)),
-                                           (5, 3, 999, dict(variant=25)), (5, 3, 999, dict(variant=27))])  # K = 125
+                                           (5, 3, 999, dict(variant=25)), (5, 3, 999, dict(variant=27)),   # K = 125
+                                           (5, 3, 999, dict(variant=28)), (5, 3, 999, dict(ctas=140, variant=28))])  # two-zone slices
 def test_partially_filled_level_blocks(gpu_lib, oracle, levels, M, B, tune):
     """Level counts that are not multiples of 32 / 64: padded lanes, a half-filled last work unit in phase C, odd
     successor ranges in phase B -- all bits must still match."""
