@@ -357,9 +357,13 @@ __device__ __forceinline__ float key2f(unsigned int k) { return __uint_as_float(
 //   pmr[q] = rd32(min_{j in block q} P[j])  (NaN ignored: a NaN candidate never wins; pad columns may hold anything finite
 //   or +Inf, they only lower a bound),  *jseed = a successor with a (nearly) smallest value -- any successor gives a valid
 //   upper bound, so a 27-bit key of the block minimum with the lane in the low bits and one REDUX.MIN are enough.
+// Layout of the block minima of the CTA's value rows: the two rows of a pair are neighbours, pm[((r >> 1) * nblk + q) * 2 +
+// (r & 1)], so that a warp that owns an even-aligned pair of rows takes both minima of a block with one 8-byte load.
+__device__ __forceinline__ int pm_idx(int r, int q, int nblk) { return (((r >> 1) * nblk + q) << 1) + (r & 1); }
+
 template <int BK>
-__device__ __forceinline__ void row_minima(const double *__restrict__ Prow, float *__restrict__ pmr, int *__restrict__ jseed, int nblk,
-                                           int lane)
+__device__ __forceinline__ void row_minima(const double *__restrict__ Prow, float *__restrict__ pm, int r, int *__restrict__ jseed,
+                                           int nblk, int lane)
 {
     static_assert(BK == 4, "two successor pairs per block");
     unsigned int key = 0xffffffffu;
@@ -370,7 +374,7 @@ __device__ __forceinline__ void row_minima(const double *__restrict__ Prow, floa
         const double m01 = fmin(w0.x, w0.y), m23 = fmin(w1.x, w1.y), m = fmin(m01, m23);
         jmin = (m == m01) ? (m == w0.x ? 0 : 1) : (m == w1.x ? 2 : 3);   // (all NaN: any successor will do)
         const float mf = __double2float_rd(m);
-        pmr[lane] = mf;
+        pm[pm_idx(r, lane, nblk)] = mf;
         key = (f2key(mf) & ~31u) | (unsigned int)lane;
     }
     const unsigned int kmin = __reduce_min_sync(0xffffffffu, key);
@@ -399,7 +403,7 @@ __device__ __forceinline__ void row_minima(const double *__restrict__ Prow, floa
 // scan the next block's candidates are loaded and added while the compare -> move chain of the current block runs.
 template <int TB, int BK, typename ArgT, bool PROF>
 __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
-                                            const float *__restrict__ cmf_l, const float *__restrict__ pmf,
+                                            const float *__restrict__ cmf_l, const float *__restrict__ pmf, int row0,
                                             const int *__restrict__ qseed, double s, float cw, float cmx, int nblk,
                                             int Kp, bool live, int rows_live, int lane, int l_self, double (&best)[TB][1],
                                             int (&arg)[TB][1], unsigned int &executed, long long (&ph)[4])
@@ -440,7 +444,7 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
         float e = __fadd_ru(__double2float_ru(__dadd_ru(ub[r], -s)), sl_l);   // >= UB - s + slack in real arithmetic
         if (!(e == e)) e = finf;                                             // NaN stage cost: prune nothing
         const float U = key2f(__reduce_max_sync(0xffffffffu, f2key(e)));
-        const float pq = pmf[r * nblk + qlane];
+        const float pq = pmf[pm_idx(row0 + r, qlane, nblk)];
         const float slq = fminf(__fmul_ru(fabsf(pq), 0x1p-30f), fmax);        // slack of the block side
         const float t = __fadd_rd(__fadd_rd(cw, pq), -slq);                   // <= cw + pm - slack in real arithmetic
         cand |= __ballot_sync(0xffffffffu, lane < nblk && !(t > U));
@@ -448,19 +452,34 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
     // ---- 3. level test (lane = level) on the candidate blocks -----------------------------------------------
     unsigned int pneed = 0;
     for (unsigned int ms = cand; ms;) {
-        int q[4];   // four candidate blocks per trip (the last one may repeat)
-        q[0] = __ffs(ms) - 1; ms &= ms - 1;
+        // four candidate blocks per trip; an exhausted mask repeats the first one (its bit is 0: no effect)
+        unsigned int bit[4];
+        int q[4];
 #pragma unroll
-        for (int k = 1; k < 4; ++k) { q[k] = ms ? __ffs(ms) - 1 : q[k - 1]; ms &= ms - 1; }
+        for (int k = 0; k < 4; ++k) {
+            bit[k] = ms & (0u - ms);
+            ms ^= bit[k];
+            q[k] = (k == 0 || bit[k]) ? 31 - __clz((int)bit[k]) : q[0];
+        }
         float a[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] = __fadd_rd(sf, cmf_l[(size_t)q[k] * Kp]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            bool nd = false;
+            // LB32 > UBf for every row of the warp: the block cannot matter to this level.  Straight-line code (no short
+            // circuit: a branch per row costs more than the add and the compare it would skip)
+            unsigned int above = 1u;
+            if constexpr (TB % 2 == 0) {
 #pragma unroll
-            for (int r = 0; r < TB; ++r) nd = nd || !(__fadd_rd(a[k], pmf[r * nblk + q[k]]) > ubf[r]);
-            pneed |= (nd ? 1u : 0u) << q[k];
+                for (int r = 0; r < TB; r += 2) {   // row0 is a multiple of TB: the pair (r, r + 1) is one 8-byte load
+                    const float2 pp = *reinterpret_cast<const float2 *>(pmf + pm_idx(row0 + r, q[k], nblk));
+                    above &= (unsigned int)(__fadd_rd(a[k], pp.x) > ubf[r]) & (unsigned int)(__fadd_rd(a[k], pp.y) > ubf[r + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < TB; ++r) above &= (unsigned int)(__fadd_rd(a[k], pmf[pm_idx(row0 + r, q[k], nblk)]) > ubf[r]);
+            }
+            pneed |= bit[k] & (above - 1u);   // above == 0: keep the block
         }
     }
     if (!live) pneed = 0;
@@ -926,7 +945,13 @@ __device__ __forceinline__ void comm_warp(const Tables &t, const WaveCfg &c, con
             }
             // the buffer the block lands in was last read by the scan of stage i + kPsBufs - 1 (or by the previous subproblem)
             const int need_scanned = hsub * (n - 1) + max(hk - (kPsBufs - 1), 0);
-            if (pred_seen >= hT && reached(scn_cnt, (unsigned int)need_scanned * (unsigned int)ncw)) {
+            // Pruned tiles with three buffers send no "scanned" signal: the block of stage i lands in the buffer stage i+2
+            // read, and a step that every warp has FINISHED has also been scanned -- step hT - 2 (or the whole previous
+            // subproblem) is complete when (hT - 1) NF arrivals have been counted.  One fence and one hand-over less per
+            // warp and stage; the block still has a whole stage to land.
+            const bool buffer_free = (c.PR > 0 && kPsBufs == 3) ? reached(fin_cnt, (unsigned int)(hT - 1) * (unsigned int)NF)
+                                                                : reached(scn_cnt, (unsigned int)need_scanned * (unsigned int)ncw);
+            if (pred_seen >= hT && buffer_free) {
                 if (lane == 0) {
                     const int i = n - hk;
                     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy read
@@ -1176,7 +1201,7 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
                     // a row group without rows (two-zone slices: this CTA owns one group less; or rows beyond the table):
                     // nothing to scan or scatter, but the warp keeps every hand-over of the stage
                     PROF_LAP(1);
-                    scanned(0);
+                    if constexpr (kPsBufs != 3) scanned(0);
                     fin.wait_inputs(i, T);
                     PROF_LAP(2);
                     finished();
@@ -1190,16 +1215,16 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
                 // block minima and seed of the rows of my row group, once per stage: the group's warps (one per level block)
                 // share its rows, then meet at the group's own named barrier (not a CTA-wide one)
                 for (int r = rowA + (tid >> 5) % nLB; r < min(rowA + TBA, fin.myR); r += nLB)
-                    row_minima<PR>(Pc + (size_t)r * Kp, pmR + r * nblk, qseed + r, nblk, lane);
+                    row_minima<PR>(Pc + (size_t)r * Kp, pmR, r, qseed + r, nblk, lane);
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + pr_grp), "r"(32 * nLB) : "memory");
                 const FinishArgs fa = fin.stage_args(sl, i, T);
                 double best[TBA][1];
                 int arg[TBA][1];
-                scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cminf + lg, pmR + rowA * nblk, qseed + rowA,
+                scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cminf + lg, pmR, rowA, qseed + rowA,
                                                  ssc[lg], sm.pminf[8 * nblk + 16 + lg], sm.pminf[8 * nblk + 16 + Kp + lg], nblk, Kp, active, pr_rows_live, lane,
                                                  min(lg, K - 1), best, arg, executed, ph);
                 PROF_LAP(1);
-                scanned(0);  // the comm warp may refill the rows this stage read
+                if constexpr (kPsBufs != 3) scanned(0);  // (three buffers: the comm warp follows the "finished" count instead)
                 fin.wait_inputs(i, T);
                 PROF_LAP(2);
                 scatter_tile<TBA, 1, ArgT>(fa, rowA, lg, best, arg);  // pad levels only write their MARK bytes
