@@ -392,8 +392,12 @@ __device__ __forceinline__ void row_minima(const double *__restrict__ Prow, floa
 //   2. row test, lane = block: block q of row r can matter to SOME level of this warp only if
 //          cw[q] + pm[q][r]  <=  max_l (UB[r][l] - s_l)
 //      -- one compare per (block, row) for the whole warp instead of one per (block, row, level).  The merge over the
-//      levels is an argument in real arithmetic, so both sides carry a slack of 2^-30 of the magnitudes involved, which
-//      covers the two fl64 roundings of a candidate (2^-52 relative) a million times over;
+//      levels is an argument in real arithmetic.  With pq = pmf[q][r] (a float, hence a double, <= every P[j] of the
+//      block) a candidate is v = fl64(fl64(s + c) + P[j]) >= fl64(fl64(s + c) + pq) by monotonicity, and that is
+//      >= s + c + pq - 2^-52 (|s| + |c|) - 2^-53 |pq| (two roundings to nearest).  The test passes only if
+//      cw + pq - 2^-30 |pq|  >  UB - s + 2^-30 (|s| + cmx)  with cw <= c and cmx >= |c|, every float operation rounded
+//      in the safe direction -- the slack covers the rounding terms a million times over, so v > UB.  Infinite and NaN
+//      operands make the comparison false or the bound infinite: nothing is pruned;
 //   3. level test, lane = level, on the blocks that survive 2.:  LB32[q][r] = rd32(rd32(sf + cmf[q][l]) + pmf[q][r]) > UBf[r]
 //      (the monotone chain of the header comment).  The masks are OR-reduced over the warp: only a warp-uniform skip
 //      saves issue slots;

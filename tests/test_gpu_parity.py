@@ -471,6 +471,34 @@ def test_pruned_scan_is_exact_and_reports_what_it_skipped(gpu_lib, oracle, kind)
     plan.close()
 
 
+@pytest.mark.parametrize("kind", ["tiny", "large", "beyond_float", "float_exact", "nan_inf"])
+def test_pruned_bound_tests_in_float_are_safe_at_extreme_magnitudes(gpu_lib, oracle, kind):
+    """The bound tests of the pruned scan run in FP32 with directed rounding.  Magnitudes far outside the float range (the
+    bounds saturate to FLT_MAX / +-Inf), far below it (float denormals, slack terms of zero), values that convert to float
+    exactly (directed rounding adds no margin, ties everywhere) and NaN / Inf stage costs must all give the reference's
+    bits: a bound may only ever be too weak."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.synthetic(n=90, B=999, seed=17, tie_heavy=(kind == "float_exact"))
+    df, beta = inst.df.copy(), inst.beta
+    if kind == "tiny":
+        df, beta = df * 1e-42, beta * 1e-42          # below the smallest normal float
+    elif kind == "large":
+        df, beta = df * 1e25, beta * 1e25
+    elif kind == "beyond_float":
+        df, beta = df * 1e200, beta * 1e200          # every value overflows float
+    elif kind == "nan_inf":
+        df[7, 1] = np.nan; df[23, 0] = np.inf; df[40, 2] = -np.inf; df[61, :] = np.nan
+    for tune in (None, dict(variant=28), dict(variant=25)):
+        try:
+            st = check_against_oracle(gpu_lib, oracle, inst.nu, inst.iterator, inst.n, inst.B, df, inst.u_old, beta, inst.p,
+                                      inst.dt, 4, radii=[999, 400, 0], tune=tune)
+        except gpu_lib.StaleCellError:
+            assert kind == "nan_inf"                 # a +Inf / NaN optimum: the library reports the reference's stale read
+            continue
+        if tune is not None:
+            assert st["prune_block"] == 4
+
+
 def _multi_case(gpu_lib, S=9, n=80, B=99):
     wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
     insts = [wl.synthetic(n=n, B=B, seed=20251018 + 2 * s, levels=3, M=3, tie_heavy=(s % 2 == 0)) for s in range(S)]
