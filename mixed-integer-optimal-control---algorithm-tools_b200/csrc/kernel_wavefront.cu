@@ -1537,7 +1537,8 @@ static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStrea
     // the cycle counters are a separate instantiation: their code would cost the production kernel ~1.5 %
     const void *fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR>
                               : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR>;
-    if constexpr (PR > 0 && TBA == 2 && TBB >= 7) {  // the tiles of the production shape: Kp as a compile-time constant
+    // the tiles of the production shape (pruned, and the exhaustive tile it falls back to): Kp as a compile-time constant
+    if constexpr ((PR > 0 && TBA == 2 && TBB >= 7) || (PR == 0 && TBA == 4 && TBB == 3 && TL == 2)) {
         if (BB_KPC != 0 && t.Kp == 128 && cfg.Kr == 128)
             fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR, 128>
                           : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 128>;
