@@ -236,7 +236,7 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *     bb200_count_updates; the difference was skipped by the bound test, results are bit-identical
  *  18 block size of the pruned scan of the current geometry (0: exhaustive scan)
  *  19 1 if the plan went back to the exhaustive tiles because its DP evaluated more candidates than the measured
- *     break-even of the pruned scan (27 %): a data / horizon dependent choice, results are identical either way
+ *     break-even of the pruned scan (25 %): a data / horizon dependent choice, results are identical either way
  *  20 CTAs that own (5) source rows; the CTAs above them own (21) rows (two-zone slices; 20 == 4: uniform slices)
  */
 int bb200_stats(bb200_plan *plan, double *out, int32_t count);

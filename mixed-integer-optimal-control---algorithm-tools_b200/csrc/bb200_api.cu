@@ -388,12 +388,11 @@ bool ensure_graph(bb200_plan *p)
 
 // The pruned scan only pays when its bound test drops most blocks; that depends on the data (jump costs against the
 // spread of the value rows, and the horizon: the first stages after the terminal one bound little).  Measured on B200
-// against the exhaustive tiles (config 4 shape, horizon sweep, profiles/prune_break_even_r02.txt): the pruned stage costs
-// 1.4 us + 12 us x (fraction of the candidates evaluated), the exhaustive one 4.56 us -- break-even near 27 %
-// (n = 100 000 evaluates 7.7 %: 2.4 us; n = 10 000 16 %: 3.35 us; n = 2 500 27 %: 4.6 us vs 4.9 us).  After a synchronised DP
-// that evaluated more, the plan goes back to the exhaustive tiles for its following DPs (TRM / a batch call the DP again
-// on similar data).
-constexpr double kPruneBreakEven = 0.27;
+// against the exhaustive tiles (config 4 shape, horizon sweep, profiles/prune_break_even_r02.txt and the final builds): the
+// pruned stage costs 1.3 us + 12 us x (fraction of the candidates evaluated), the exhaustive one 4.3 us -- break-even at
+// 25 % (n = 100 000 evaluates 7.7 %: 2.2 us; n = 10 000 16 %; n = 2 500 27 %).  After a synchronised DP that evaluated more,
+// the plan goes back to the exhaustive tiles for its following DPs (TRM / a batch call the DP again on similar data).
+constexpr double kPruneBreakEven = 0.25;
 void adapt_pruning(bb200_plan *p, int slots, unsigned long long executed)
 {
     if (!p->wave_ok || p->cfg.PR == 0 || p->tune_variant != 0 || p->prune_off) return;
