@@ -234,7 +234,8 @@ int bb200_tv(bb200_plan *plan, int32_t slot, double p, double *tv);
  *  15 waves of that call            16 host waits (event synchronisations) of all batched calls so far
  *  17 candidates the last DP really evaluated when it ran the pruned scan (else 0): the exhaustive count is
  *     bb200_count_updates; the difference was skipped by the bound test, results are bit-identical
- *  18 block size of the pruned scan of the current geometry (0: exhaustive scan)
+ *  18 block size of the pruned scan of the current geometry (0: exhaustive scan); also 4 while a wide level set runs the
+ *     per-stage kernels with the pruned scan
  *  19 1 if the plan went back to the exhaustive tiles because its DP evaluated more candidates than the measured
  *     break-even of the pruned scan (25 %): a data / horizon dependent choice, results are identical either way
  *  20 CTAs that own (5) source rows; the CTAs above them own (21) rows (two-zone slices; 20 == 4: uniform slices)

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbellman_b200.so")
-SOURCES = ["bb200_api.cu", "bb200_multi.cu", "kernels_common.cu", "kernel_wavefront.cu", "kernels_microbench.cu"]
-HEADERS = ["bb200_internal.cuh", "kernels.cuh", os.path.join("..", "..", "include", "bellman_b200.h")]
+SOURCES = ["bb200_api.cu", "bb200_multi.cu", "kernels_common.cu", "kernel_wavefront.cu", "kernel_stage_pruned.cu", "kernels_microbench.cu"]
+HEADERS = ["bb200_internal.cuh", "kernels.cuh", "pruned_scan.cuh", os.path.join("..", "..", "include", "bellman_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",  # B200 only; no other arch, no PTX fallback
     "-O3", "-lineinfo", "-std=c++17",

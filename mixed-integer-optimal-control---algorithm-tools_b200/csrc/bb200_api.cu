@@ -75,6 +75,10 @@ struct bb200_plan {
     unsigned long long *h_exec = nullptr;  // pinned copy, fetched with the error words
     int last_dp_slots = 1;                 // slots of the last DP launch (the counter above sums over them)
     bool prune_off = false;                // the pruned scan did not pay on this plan's data: exhaustive tiles from now on
+    // per-stage kernels with the pruned scan (level sets the pipelined kernel does not take)
+    void *d_sp = nullptr;
+    StagePrunedTabs sp{};
+    bool sp_ok = false, sp_off = false;
     double prune_switches = 0.;
     long long *d_prof = nullptr;
     bool prof_on = false;
@@ -178,6 +182,7 @@ int reconfigure(bb200_plan *p)
 {
     p->wave_ok = false;
     p->mini_ok = false;
+    p->sp_ok = false;
     if (p->flags & BB200_FLAG_STAGE_KERNELS) return BB200_OK;
     // small stages: one CTA per subproblem, rows in shared memory (unless a wavefront geometry was requested)
     if (!(p->tune_ctas || p->tune_js || p->tune_variant) && !(p->flags & BB200_FLAG_FORCE_WAVEFRONT) &&
@@ -212,6 +217,22 @@ int reconfigure(bb200_plan *p)
         p->cfg = c;
         p->wave_ok = true;
         pin_ring_in_l2(p);
+    } else if (!(p->tune_ctas || p->tune_js || p->tune_variant) && stage_pruned_applicable(p->tab)) {
+        // one launch per stage, but with the branch-and-bound scan (kernel_stage_pruned.cu); its tables are built once
+        if (!p->d_sp) {
+            const size_t bytes = stage_pruned_table_bytes(p->tab);
+            if (cudaMalloc(&p->d_sp, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                p->d_sp = nullptr;
+                return BB200_OK;  // no tables: the plain per-stage kernels still run
+            }
+            p->dev_bytes += bytes;
+            if (stage_pruned_setup(p->tab, p->d_sp, p->sp, p->stream) != cudaSuccess) {
+                cudaGetLastError();
+                return BB200_OK;
+            }
+        }
+        p->sp_ok = true;
     }
     return BB200_OK;
 }
@@ -240,6 +261,7 @@ void destroy_plan(bb200_plan *p)
     if (p->ev_prep) cudaEventDestroy(p->ev_prep);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     cudaFree(p->d_lvd); cudaFree(p->d_cost); cudaFree(p->d_halo); cudaFree(p->d_scalar);
+    if (p->d_sp) cudaFree(p->d_sp);
     cudaFree(p->d_goff); cudaFree(p->d_flags); cudaFree(p->d_err); cudaFree(p->d_btmax); cudaFree(p->d_exec);
     cudaFree(p->d_slots);
     cudaFree(p->d_prof);
@@ -307,7 +329,8 @@ int queue_dp(bb200_plan *p, int slot0, int count, bool capturing = false, cudaEv
         p->last_path = 1;
     } else {
         for (int s = slot0; s < slot0 + count; ++s) {
-            int l = launch_stage_path(p->tab, p->slots_dev[s], p->argw, st);
+            int l = (p->sp_ok && !p->sp_off) ? launch_stage_pruned_path(p->tab, p->slots_dev[s], p->argw, p->sp, p->d_exec, st)
+                                             : launch_stage_path(p->tab, p->slots_dev[s], p->argw, st);
             if (l < 0) return fail(BB200_ERR_ARG, "shape not supported by the per-stage kernels (K=%d)", p->K);
             p->launches += l;
         }
@@ -393,8 +416,20 @@ bool ensure_graph(bb200_plan *p)
 // 25 % (n = 100 000 evaluates 7.7 %: 2.2 us; n = 10 000 16 %; n = 2 500 27 %).  After a synchronised DP that evaluated more,
 // the plan goes back to the exhaustive tiles for its following DPs (TRM / a batch call the DP again on similar data).
 constexpr double kPruneBreakEven = 0.25;
+// (The per-stage pruned kernels pay for their bound tests with fewer candidates too: past half of them the plain
+// per-stage kernels take over.)
+constexpr double kStagePruneBreakEven = 0.5;
 void adapt_pruning(bb200_plan *p, int slots, unsigned long long executed)
 {
+    if (p->sp_ok && !p->sp_off && !p->wave_ok && !p->mini_ok) {
+        const double full = (double)(p->n > 1 ? p->n - 1 : 1) * p->B1 * (double)p->Kp * p->K * slots;
+        if ((double)executed > kStagePruneBreakEven * full) {
+            p->sp_off = true;
+            p->prune_switches += 1;
+            if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }  // the launches are baked in
+        }
+        return;
+    }
     if (!p->wave_ok || p->cfg.PR == 0 || p->tune_variant != 0 || p->prune_off) return;
     const double full = (double)(p->n > 1 ? p->n - 1 : 1) * p->B1 * (double)p->cfg.Kr * p->K * slots;
     if ((double)executed > kPruneBreakEven * full) {
@@ -1099,7 +1134,8 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
     if (!plan || !out) return fail(BB200_ERR_ARG, "bad arguments");
     Guard g(plan);
     unsigned long long exec = 0;
-    if (count > 17 && plan->cfg.PR > 0 && plan->wave_ok) {
+    const bool sp_on = plan->sp_ok && !plan->sp_off && !plan->wave_ok && !plan->mini_ok;
+    if (count > 17 && ((plan->cfg.PR > 0 && plan->wave_ok) || sp_on)) {
         CU(cudaStreamSynchronize(plan->stream));
         CU(cudaMemcpy(&exec, plan->d_exec, sizeof exec, cudaMemcpyDeviceToHost));
     }
@@ -1110,7 +1146,7 @@ int bb200_stats(bb200_plan *plan, double *out, int32_t count)
                           plan->last_wave_ms, plan->graph_replays,
                           plan->wave_ok ? (double)(plan->cfg.variant + 1) : 0., plan->wave_ok ? (double)plan->cfg.NS : 0.,
                           plan->last_batch_ms, plan->batch_waves, plan->batch_syncs, (double)exec,
-                          plan->wave_ok ? (double)plan->cfg.PR : 0., plan->prune_switches,
+                          plan->wave_ok ? (double)plan->cfg.PR : (sp_on ? 4. : 0.), plan->prune_switches,
                           plan->wave_ok ? (double)plan->cfg.GA : 0., plan->wave_ok ? (double)plan->cfg.Rtop : 0.};
     for (int k = 0; k < count && k < 22; ++k) out[k] = v[k];
     return BB200_OK;

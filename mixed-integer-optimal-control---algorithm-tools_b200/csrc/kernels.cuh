@@ -7,6 +7,21 @@ namespace bb200 {
 // kernels_common.cu
 void launch_prep(const Tables &t, const SlotDev &slot, int *err, int *btmax, cudaStream_t st);
 int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream_t st);
+int launch_terminal_stage(const Tables &t, const SlotDev &slot, cudaStream_t st);  // the terminal stage alone (1 launch; -1: K > 1024)
+
+// kernel_stage_pruned.cu -- per-stage kernels with the branch-and-bound scan, for level sets the pipelined kernel does not take
+struct StagePrunedTabs {
+    double *cpad;   // [Kp][Kp] jump costs, +Inf rows K .. Kp-1
+    float *cminf;   // [nblk][Kp] block minima of the jump costs, rounded down
+    float *cwv;     // [Kp/32][nblk] per level block: smallest cminf over its live levels
+    float *cmx;     // [Kp] largest finite |jump cost| into a level, rounded up
+    int nblk;       // blocks of 4 successors = Kp / 4
+};
+bool stage_pruned_applicable(const Tables &t);
+size_t stage_pruned_table_bytes(const Tables &t);
+cudaError_t stage_pruned_setup(const Tables &t, void *base, StagePrunedTabs &pt, cudaStream_t st);
+int launch_stage_pruned_path(const Tables &t, const SlotDev &slot, int argw, const StagePrunedTabs &pt, unsigned long long *exec,
+                             cudaStream_t st);
 bool mini_applicable(const Tables &t, size_t smem_max);
 cudaError_t launch_mini(const Tables &t, const SlotDev *d_slots, int count, int argw, cudaStream_t st);
 // sweep == nullptr: one CTA for `slot`; otherwise `ctas` = slots * radii CTAs, one per (slot, radius) of the sweep

@@ -568,6 +568,16 @@ void launch_prep(const Tables &t, const SlotDev &slot, int *err, int *btmax, cud
     prep_kernel<<<blocks, threads, 0, st>>>(t, slot, err, btmax);
 }
 
+int launch_terminal_stage(const Tables &t, const SlotDev &slot, cudaStream_t st)
+{
+    int bx = ((t.K + 31) / 32) * 32;
+    if (bx > 1024) return -1;
+    int by = 1024 / bx;
+    if (by > 8) by = 8;
+    terminal_kernel<<<dim3((t.B1 + by - 1) / by), dim3(bx, by), 0, st>>>(t, slot, (t.n + 1) & 1);
+    return 1;
+}
+
 int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream_t st)
 {
     // blockDim.x = levels rounded to a warp, blockDim.y = source rows
@@ -577,9 +587,7 @@ int launch_stage_path(const Tables &t, const SlotDev &slot, int argw, cudaStream
     if (by > 8) by = 8;
     dim3 block(bx, by);
     dim3 grid((t.B1 + by - 1) / by);
-    int launches = 0;
-    terminal_kernel<<<grid, block, 0, st>>>(t, slot, (t.n + 1) & 1);
-    ++launches;
+    int launches = launch_terminal_stage(t, slot, st);
     for (int i = t.n - 1; i >= 1; --i) {
         if (argw == 1) stage_kernel<uint8_t><<<grid, block, 0, st>>>(t, slot, i);
         else stage_kernel<uint16_t><<<grid, block, 0, st>>>(t, slot, i);

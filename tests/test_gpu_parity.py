@@ -367,6 +367,38 @@ def test_uint16_argmin_and_large_level_sets(gpu_lib, oracle):
     plan.close()
 
 
+@pytest.mark.parametrize("levels,M,n,B", [(6, 3, 50, 211), (16, 2, 40, 97), (7, 3, 24, 60), (15, 2, 30, 333)])
+@pytest.mark.parametrize("kind", ["random", "ties", "far", "flat"])
+def test_wide_level_sets_run_the_pruned_per_stage_kernels(gpu_lib, oracle, levels, M, n, B, kind):
+    """K = 216, 256, 343 (uint16 argmin), 225: the jump-cost table does not fit in shared memory, so the DP runs one launch
+    per stage -- with the same branch-and-bound scan as the pipelined kernel, the successor axis in segments of 32 blocks
+    (kernel_stage_pruned.cu).  Bits must match the oracle; data on which the bound test drops nothing ("flat") sends the plan
+    back to the plain per-stage kernels, which must give the same bits again."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    inst = wl.synthetic(n=n, B=B, seed=levels * 10 + M, levels=levels, M=M, tie_heavy=(kind == "ties"))
+    beta = {"ties": 0.25, "random": 0.5, "flat": 0.0, "far": 50.0}[kind]
+    df = inst.df if kind != "flat" else np.zeros_like(inst.df)
+    plan = gpu_lib.TRMPlan(inst.nu, inst.iterator, n, B, beta, inst.p, inst.dt)
+    U, Phi, n_upd = oracle_tables(oracle, inst.nu, inst.iterator, n, B, df, inst.u_old, beta, inst.p, inst.dt, plan.cost)
+    for rep in range(2):                                   # the second DP may run on the plain kernels (adaptive switch)
+        plan.bellman(df, inst.u_old)
+        st = plan.stats()
+        assert int(st["path"]) == 0 and int(st["arg_bytes"]) == (2 if inst.K > 255 else 1)
+        if rep == 0:   # the first DP ran the pruned kernels (and may have switched the plan back to the plain ones afterwards)
+            assert int(st["prune_block"]) == 4 or st["prune_switched_off"] >= 1
+        np.testing.assert_array_equal(plan.export_phi(), Phi)
+        np.testing.assert_array_equal(plan.export_argmin(1, n, fill=0), U)
+        assert plan.count_updates() == n_upd
+        for Bn in (B, B // 3, 0):
+            u, ur = np.zeros((n, M)), np.zeros((n, M))
+            plan.eval_u(u, Bn)
+            oracle.eval_u_TRM(ur, inst.u_old, U, Phi, Bn, inst.nu)
+            np.testing.assert_array_equal(u, ur)
+    if kind == "flat":
+        assert plan.stats()["prune_switched_off"] >= 1 and int(plan.stats()["prune_block"]) == 0
+    plan.close()
+
+
 def test_resident_interface_multiple_slots_one_launch(gpu_lib, oracle):
     """bench.py's path: inputs uploaded once, several subproblems walked by ONE persistent launch."""
     wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
