@@ -1357,6 +1357,10 @@ static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStrea
             fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR, 128>
                           : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 128>;
     }
+    if constexpr (PR > 0 && TBA == 2 && TBB == 8) {  // the other level counts the pruned tiles take: 64 < K <= 96, K = 64
+        if (BB_KPC != 0 && !cfg.prof && t.Kp == 96 && cfg.Kr == 96) fn = (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 96>;
+        if (BB_KPC != 0 && !cfg.prof && t.Kp == 64 && cfg.Kr == 64) fn = (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 64>;
+    }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     // cooperative launch: the CTAs wait on one another, so all of them must be co-resident

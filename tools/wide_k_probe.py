@@ -1,6 +1,7 @@
 """Throughput of the DP on level sets the pipelined kernel does not take (jump-cost table larger than shared memory,
-K > 150; uint16 argmin, K > 255): these shapes run one launch per stage (stage_kernel), and with K^2 candidates per cell a
-stage is long enough for the launch overhead not to matter.  Usage: python tools/wide_k_probe.py"""
+K > 150; uint16 argmin, K > 255): these shapes run one launch per stage -- with the pruned scan (kernel_stage_pruned.cu)
+unless the plan was created with BB200_FLAG_STAGE_KERNELS.  With K^2 candidates per cell a stage is long enough for the
+launch overhead not to matter.  Usage: python tools/wide_k_probe.py [plain]"""
 import importlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,7 +12,7 @@ wl = importlib.import_module(m.__name__ + ".workloads")
 print(f"{'shape':28s} {'K':>4s} {'path':>5s} {'arg bytes':>9s} {'updates':>10s} | {'DP ms':>9s} {'us/stage':>9s} {'T upd/s':>8s}")
 for levels, M, n in ((5, 3, 2000), (6, 3, 2000), (7, 3, 1000), (16, 2, 1000)):
     inst = wl.synthetic(n=n, B=999, seed=11, levels=levels, M=M)
-    plan = m.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt)
+    plan = m.TRMPlan(inst.nu, inst.iterator, inst.n, inst.B, inst.beta, inst.p, inst.dt, flags=(1 if 'plain' in sys.argv and inst.K > 150 else 0))
     plan.upload(0, inst.df, inst.u_old)
     for _ in range(2):
         plan.bellman_resident(0, 1); plan.sync()
