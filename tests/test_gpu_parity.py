@@ -203,6 +203,44 @@ def test_n_equals_one_and_two(gpu_lib, oracle):
             plan.close()
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
+def test_shortest_horizons_on_the_pruned_production_geometry(gpu_lib, oracle, n):
+    """n = 1 .. 5 on the config-4 shape with the pruned tiles forced (148 CTAs, two-zone slices, three value-row buffers, no
+    'scanned' hand-over): the halo / cost cursors of the comm warp and the barrier phases start and end within a few steps;
+    three subproblems walked by ONE launch exercise the hand-over from one subproblem to the next."""
+    wl = importlib.import_module(gpu_lib.__name__ + ".workloads")
+    insts = [wl.synthetic(n=n, B=999, seed=40 + s, tie_heavy=(s == 1)) for s in range(3)]
+    base = insts[0]
+    plan = gpu_lib.TRMPlan(base.nu, base.iterator, n, base.B, base.beta, base.p, base.dt, flags=4, batch=3)
+    plan.tune(variant=28)
+    for s, inst in enumerate(insts):
+        plan.upload(s, inst.df, inst.u_old)
+    plan.bellman_resident(0, 3)
+    plan.sync()
+    st = plan.stats()
+    assert int(st["path"]) == 1 and int(st["prune_block"]) == 4 and int(st["ctas"]) == 148
+    for s, inst in enumerate(insts):
+        U, Phi, n_upd = oracle_tables(oracle, inst.nu, inst.iterator, n, inst.B, inst.df, inst.u_old, base.beta, base.p, base.dt,
+                                      plan.cost)
+        got = plan.export_phi(s)
+        np.testing.assert_array_equal(got[0], Phi[0])
+        if n > 1:
+            np.testing.assert_array_equal(got[1], Phi[1])
+            np.testing.assert_array_equal(plan.export_argmin(1, n, fill=0, slot=s), U)
+        for Bn in (999, 5, 0):
+            u, ur = np.zeros((n, 3)), np.zeros((n, 3))
+            try:
+                plan.backtrack_resident(s, Bn); plan.sync()
+                plan.download(s, u)
+            except gpu_lib.StaleCellError:
+                with pytest.raises(IndexError):
+                    oracle.eval_u_TRM(ur, inst.u_old, U, Phi, Bn, inst.nu)
+                continue
+            oracle.eval_u_TRM(ur, inst.u_old, U, Phi, Bn, inst.nu)
+            np.testing.assert_array_equal(u, ur)
+    plan.close()
+
+
 def test_error_behaviour(gpu_lib):
     m = gpu_lib
     nu = [[0, 1]]
