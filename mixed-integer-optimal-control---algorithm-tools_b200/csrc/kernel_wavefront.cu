@@ -1104,6 +1104,7 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
         }
     }
     if (PROF && c.prof && tid == 0 && self_finish) {
+        c.prof[(size_t)g * 16 + 13] = fin.ring_wait;  // the part of the hand-over spent waiting for ring space
         c.prof[(size_t)g * 16 + 14] = fin.pcc[0];
         c.prof[(size_t)g * 16 + 15] = fin.pcc[1];
     }
