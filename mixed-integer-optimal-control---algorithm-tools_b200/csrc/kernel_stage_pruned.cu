@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(512) stage_pruned_kernel(Tables t, SlotDev slo
     const double *cs_l = pt.cpad + lc;
     const float *cmf_l = pt.cminf + lc;
     PrunedBounds<TB> pb;
-    pruned_bounds<TB>(Ps + 0, cs_l, jseed, s, pt.cmx[lc], Kp, live, rows_live, lc, pb);
+    double vself[TB];
+    pruned_self_candidates<TB>(Ps, cs_l, s, Kp, lc, vself);
+    pruned_bounds<TB>(Ps, cs_l, jseed, s, pt.cmx[lc], Kp, live, rows_live, vself, pb);
     double best[TB][1];
     int arg[TB][1];
 #pragma unroll

@@ -334,7 +334,7 @@ template <int TB, int BK, typename ArgT, bool PROF>
 __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, const double *__restrict__ cs_l,
                                             const float *__restrict__ cmf_l, const float *__restrict__ pmf, int row0,
                                             const int *__restrict__ qseed, double s, float cw, float cmx, int nblk,
-                                            int Kp, bool live, int rows_live, int lane, int l_self, double (&best)[TB][1],
+                                            int Kp, bool live, int rows_live, int lane, const double (&vself)[TB], double (&best)[TB][1],
                                             int (&arg)[TB][1], unsigned int &executed, long long (&ph)[4])
 {
     constexpr int MARKI = (int)(ArgT) ~(ArgT)0;
@@ -342,7 +342,7 @@ __device__ __forceinline__ void scan_pruned(const double *__restrict__ Prow, con
     if constexpr (PROF) tq = clock64();
 #define PH_LAP(k) do { if constexpr (PROF) { const long long tn = clock64(); ph[k] += tn - tq; tq = tn; } } while (0)
     PrunedBounds<TB> pb;
-    pruned_bounds<TB>(Prow, cs_l, qseed, s, cmx, Kp, live, rows_live, l_self, pb);
+    pruned_bounds<TB>(Prow, cs_l, qseed, s, cmx, Kp, live, rows_live, vself, pb);
     PH_LAP(1);
 #pragma unroll
     for (int r = 0; r < TB; ++r) { best[r][0] = d_inf(); arg[r][0] = MARKI; }
@@ -1034,13 +1034,17 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
                 // share its rows, then meet at the group's own named barrier (not a CTA-wide one)
                 for (int r = rowA + (tid >> 5) % nLB; r < min(rowA + TBA, fin.myR); r += nLB)
                     row_minima<PR>(Pc + (size_t)r * Kp, pmR, r, qseed + r, nblk, lane);
+                // the no-jump candidates need neither minima nor seeds: their loads and adds run while the group gathers
+                const double s_l = ssc[lg];
+                double vself[TBA];
+                pruned_self_candidates<TBA>(Pc + (size_t)rowA * Kp, sm.cs + lg, s_l, Kp, min(lg, K - 1), vself);
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + pr_grp), "r"(32 * nLB) : "memory");
                 const FinishArgs fa = fin.stage_args(sl, i, T);
                 double best[TBA][1];
                 int arg[TBA][1];
                 scan_pruned<TBA, PR, ArgT, PROF>(Pc + (size_t)rowA * Kp, sm.cs + lg, sm.cminf + lg, pmR, rowA, qseed + rowA,
-                                                 ssc[lg], sm.pminf[8 * nblk + 16 + lg], sm.pminf[8 * nblk + 16 + Kp + lg], nblk, Kp, active, pr_rows_live, lane,
-                                                 min(lg, K - 1), best, arg, executed, ph);
+                                                 s_l, sm.pminf[8 * nblk + 16 + lg], sm.pminf[8 * nblk + 16 + Kp + lg], nblk, Kp, active, pr_rows_live, lane,
+                                                 vself, best, arg, executed, ph);
                 PROF_LAP(1);
                 if constexpr (kPsBufs != 3) scanned(0);  // (three buffers: the comm warp follows the "finished" count instead)
                 fin.wait_inputs(i, T);

@@ -95,20 +95,30 @@ struct PrunedBounds {
     float sf;        // stage cost rounded down to float
 };
 
+// The no-jump candidates j = l of a tile: they need neither the block minima nor the seeds, so a caller that has to wait for
+// those (a barrier) can evaluate them first.
+template <int TB>
+__device__ __forceinline__ void pruned_self_candidates(const double *__restrict__ Prow, const double *__restrict__ cs_l, double s, int Kp,
+                                                       int l_self, double (&vself)[TB])
+{
+    const double a = __dadd_rn(s, cs_l[(size_t)l_self * Kp]);
+#pragma unroll
+    for (int r = 0; r < TB; ++r) vself[r] = __dadd_rn(a, Prow[(size_t)r * Kp + l_self]);
+}
+
 template <int TB>
 __device__ __forceinline__ void pruned_bounds(const double *__restrict__ Prow, const double *__restrict__ cs_l,
                                               const int *__restrict__ qseed, double s, float cmx, int Kp, bool live,
-                                              int rows_live, int l_self, PrunedBounds<TB> &pb)
+                                              int rows_live, const double (&vself_in)[TB], PrunedBounds<TB> &pb)
 {
     const double inf = d_inf();
     const float finf = __int_as_float(0x7f800000);
     // ---- 1. upper bounds ---------------------------------------------------------------------------------
-    const double cself = cs_l[(size_t)l_self * Kp];
 #pragma unroll
     for (int r = 0; r < TB; ++r) {
         const int js = qseed[r];
         const double vseed = __dadd_rn(__dadd_rn(s, cs_l[(size_t)js * Kp]), Prow[(size_t)r * Kp + js]);
-        const double vself = __dadd_rn(__dadd_rn(s, cself), Prow[(size_t)r * Kp + l_self]);
+        const double vself = vself_in[r];
         double u = inf;               // from +Inf with '>', so that a NaN candidate is ignored
         if (u > vseed) u = vseed;
         if (u > vself) u = vself;
