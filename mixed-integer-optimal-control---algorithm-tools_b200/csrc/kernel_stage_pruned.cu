@@ -2,7 +2,7 @@
 // kernel does not take: a jump-cost table larger than shared memory (K > ~150) or a uint16 argmin table (K > 255).
 //
 // Same I/O as stage_kernel (kernels_common.cu): one launch per stage i = n-1 .. 1, value rows ping-pong in the exit-state
-// buffers of the slot, no inter-CTA synchronisation at all.  A CTA owns TB = 2 consecutive SOURCE budget rows and all
+// buffers of the slot, no inter-CTA synchronisation at all.  A CTA owns TB = 4 consecutive SOURCE budget rows and all
 // levels (thread = level, warp = 32 levels); the rows are staged in shared memory, the jump costs c[j][l] stay in global
 // memory (a few hundred KB, L2 resident; lanes read consecutive levels: coalesced) in a copy padded with +Inf rows up to
 // whole blocks, and the successor axis is walked in segments of 32 blocks with pruned_segment (pruned_scan.cuh): the
@@ -14,7 +14,7 @@
 
 namespace bb200 {
 
-constexpr int kSpTB = 2;   // source rows per CTA
+constexpr int kSpTB = 4;   // source rows per CTA
 constexpr int kSpBK = 4;   // successors per block
 
 // Per-plan tables (built once per plan from the jump-cost table):
