@@ -1131,14 +1131,14 @@ __device__ __forceinline__ void wavefront_body(const Tables &t, const WaveCfg &c
 #undef PROF_LAP
 }
 
-template <int TBA, int TBB, int TL, typename ArgT, int MAXT, bool PROF, int PR, int KPC = 0>
+template <int TBA, int TBB, int TL, typename ArgT, int MAXT, bool PROF, int PR, int KPC = 0, int KRC = KPC>
 __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(const __grid_constant__ Tables t_in, const __grid_constant__ WaveCfg c_in)
 {
     if constexpr (KPC > 0) {
         Tables t = t_in;
         WaveCfg c = c_in;
         t.Kp = KPC;
-        c.Kr = KPC;
+        c.Kr = KRC;   // rows of the (padded) jump-cost table: Kp for pruned tiles, the j-groups' whole trips for exhaustive ones
         wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t, c);
     } else {
         wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t_in, c_in);
@@ -1361,6 +1361,10 @@ static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStrea
         if (BB_KPC != 0 && t.Kp == 128 && cfg.Kr == 128)
             fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR, 128>
                           : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 128>;
+    }
+    if constexpr (PR == 0 && (TBA == 1 || TBA == 2 || TBA == 4) && TBB == 0 && TL == 1) {  // the reference's heat example: 6 x 6 levels, one j-group (direct tiles)
+        if (BB_KPC != 0 && !cfg.prof && t.Kp == 64 && cfg.Kr == 40 && cfg.JS == 1 && cfg.NS == 0)
+            fn = (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 64, 40>;
     }
     if constexpr (PR > 0 && TBA == 2 && TBB == 8) {  // the other level counts the pruned tiles take: 64 < K <= 96, K = 64
         if (BB_KPC != 0 && !cfg.prof && t.Kp == 96 && cfg.Kr == 96) fn = (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 96>;
