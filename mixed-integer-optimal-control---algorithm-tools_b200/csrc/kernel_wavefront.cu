@@ -1139,6 +1139,7 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(const __grid_constan
         WaveCfg c = c_in;
         t.Kp = KPC;
         c.Kr = KRC;   // rows of the (padded) jump-cost table: Kp for pruned tiles, the j-groups' whole trips for exhaustive ones
+        if constexpr (PR > 0) { c.R = TBB; c.RA = TBB; c.JS = 1; c.NS = 0; c.RB = 0; }  // what fill_geometry sets for pruned tiles anyway
         wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t, c);
     } else {
         wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t_in, c_in);
