@@ -1140,6 +1140,10 @@ __global__ void __launch_bounds__(MAXT, 1) wavefront_kernel(const __grid_constan
         t.Kp = KPC;
         c.Kr = KRC;   // rows of the (padded) jump-cost table: Kp for pruned tiles, the j-groups' whole trips for exhaustive ones
         if constexpr (PR > 0) { c.R = TBB; c.RA = TBB; c.JS = 1; c.NS = 0; c.RB = 0; }  // what fill_geometry sets for pruned tiles anyway
+        if constexpr (PR == 0 && TBA == 4 && TBB == 3 && TL == 2 && KPC == 128) {
+            // the config-4 geometry of the exhaustive tile (launch_variant checks that the plan's geometry is this one)
+            c.JS = 4; c.jper = 32; c.NS = 6; c.NF = 6; c.RG = 1; c.R = 7; c.RA = 4; c.RB = 3; c.tpg = 64; c.nLG = 63; c.EC = 2;
+        }
         wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t, c);
     } else {
         wavefront_body<TBA, TBB, TL, ArgT, PROF, PR>(t_in, c_in);
@@ -1359,7 +1363,9 @@ static cudaError_t launch_variant(const Tables &t, const WaveCfg &cfg, cudaStrea
                               : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR>;
     // the tiles of the production shape (pruned, and the exhaustive tile it falls back to): Kp as a compile-time constant
     if constexpr ((PR > 0 && TBA == 2 && TBB >= 7) || (PR == 0 && TBA == 4 && TBB == 3 && TL == 2)) {
-        if (BB_KPC != 0 && t.Kp == 128 && cfg.Kr == 128)
+        const bool geom_ok = PR > 0 || (cfg.JS == 4 && cfg.jper == 32 && cfg.NS == 6 && cfg.NF == 6 && cfg.RG == 1 && cfg.R == 7 &&
+                                        cfg.RA == 4 && cfg.RB == 3 && cfg.tpg == 64 && cfg.nLG == 63 && cfg.EC == 2);
+        if (BB_KPC != 0 && t.Kp == 128 && cfg.Kr == 128 && geom_ok)
             fn = cfg.prof ? (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, true, PR, 128>
                           : (const void *)wavefront_kernel<TBA, TBB, TL, uint8_t, MAXT, false, PR, 128>;
     }
