@@ -3,9 +3,9 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "mixed-integer-optimal-control---algorithm-tools_b200", "libbellman_b200.so")
 KERNELS = [("pruned tiles, production default at config 4: wavefront_kernel<2,8,1,u8,640,false,4,128> (two-zone slices, compile-time level count)",
-            "_ZN5bb20016wavefront_kernelILi2ELi8ELi1EhLi640ELb0ELi4ELi128EEEvNS_6TablesENS_7WaveCfgE"),
+            "_ZN5bb20016wavefront_kernelILi2ELi8ELi1EhLi640ELb0ELi4ELi128ELi128EEEvNS_6TablesENS_7WaveCfgE"),
            ("exhaustive tiles (fallback when the bound test does not pay): wavefront_kernel<4,3,2,u8,512,false,0>",
-            "_ZN5bb20016wavefront_kernelILi4ELi3ELi2EhLi512ELb0ELi0ELi0EEEvNS_6TablesENS_7WaveCfgE")]
+            "_ZN5bb20016wavefront_kernelILi4ELi3ELi2EhLi512ELb0ELi0ELi0ELi0EEEvNS_6TablesENS_7WaveCfgE")]
 WANT = re.compile(r"^(@!?U?P\d )?(DADD|DSETP|DMUL|DFMA|FADD|FMUL|FSETP|FMNMX|F2F|FSEL|SEL|MOV|IMAD\.MOV|LDS|STS|STG|LDG|LDL|STL|UBLKCP|SYNCS|MEMBAR|FENCE|BAR|CREDUX|REDUX|VOTE|NANOSLEEP|HMMA|UTC|WARPSYNC|CCTL|ERRBAR|CGAERRBAR)")
 out = ["# SASS evidence, round 2 final build (cuobjdump -sass libbellman_b200.so, sm_100a, nvcc 12.9; tools/sass_evidence.py)", ""]
 for title, sym in KERNELS:
